@@ -1,0 +1,123 @@
+/* librvcb200 -- C ABI of the B200-native RVC inference hot path.
+ *
+ * The reference (fumiama/Retrieval-based-Voice-Conversion-WebUI) has no FFI/plugin
+ * interface: its seams are duck-typed Python objects.  This header is
+ * the boundary a maintainer binds *immediately beneath* those Python seams; each entry point
+ * names the reference interface it replaces.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions: plain pointers and sizes only; pointers prefixed d_ are DEVICE pointers owned
+ * by the caller; `stream` is a cudaStream_t passed as void*; every function returns 0 on
+ * success and a negative code on failure with the message available from rvcb_last_error();
+ * no C++ exception crosses the ABI; a handle is safe for one caller at a time
+ * (the reference's own threading model: SURVEY.md 8b "Threading").
+ */
+#ifndef RVCB200_H
+#define RVCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rvcb_weights rvcb_weights;
+typedef struct rvcb_hubert rvcb_hubert;
+typedef struct rvcb_index rvcb_index;
+typedef struct rvcb_rmvpe rvcb_rmvpe;
+typedef struct rvcb_synth rvcb_synth;
+
+/* ---- runtime ---------------------------------------------------------------------------- */
+int rvcb_init(int device);                 /* cudaSetDevice + capability check (sm_100 required) */
+const char* rvcb_last_error(void);
+unsigned long long rvcb_launch_count(void); /* kernels launched by this library so far */
+const char* rvcb_version(void);
+
+/* ---- weight container (host fp32 tensors keyed by the reference's state_dict names) ------
+ * replaces: torch.load + load_state_dict in rvc/synthesizer.py:10-35, rvc/f0/models.py:9-11,
+ * infer/modules/vc/utils.py:24-36 (the Python side reads the .pth/.pt and hands tensors over). */
+int rvcb_weights_create(rvcb_weights** out);
+int rvcb_weights_add(rvcb_weights* w, const char* name, const float* host_data, int ndim, const int64_t* shape);
+void rvcb_weights_destroy(rvcb_weights* w);
+
+/* ---- HuBERT-base content features -----------------------------------------------------------
+ * replaces: fairseq HubertModel.extract_features(source, padding_mask, output_layer)
+ * called at infer/modules/vc/pipeline.py:102-110, infer/lib/rtrvc.py:154-162 and
+ * .final_proj (v1, pipeline.py:110). */
+int rvcb_hubert_create(const rvcb_weights* w, rvcb_hubert** out);
+int rvcb_hubert_num_frames(int n_samples);
+/* d_wav: f32[n_samples]; d_out: f32[T_h, 768]; returns T_h through n_frames */
+int rvcb_hubert_extract_features(rvcb_hubert* h, const float* d_wav, int n_samples, int output_layer,
+                                 float* d_out, int* n_frames, void* stream);
+/* d_in f32[T,768] -> d_out f32[T,256] */
+int rvcb_hubert_final_proj(rvcb_hubert* h, const float* d_in, int T, float* d_out, void* stream);
+void rvcb_hubert_destroy(rvcb_hubert* h);
+
+/* ---- IVF-Flat retrieval ---------------------------------------------------------------------
+ * replaces: faiss.read_index(...).search(npy, k=8) / reconstruct_n and the numpy blend at
+ * infer/modules/vc/pipeline.py:113-138, infer/lib/rtrvc.py:169-185. */
+int rvcb_index_create(const float* centroids, int nlist, const float* vectors, int64_t ntotal, int d,
+                      const int64_t* list_off /*[nlist+1]*/, const int64_t* list_ids /*[ntotal]*/,
+                      rvcb_index** out);
+int64_t rvcb_index_ntotal(const rvcb_index* ix);
+/* nprobe = 1.  d_q f32[nq,d] -> d_D f32[nq,k] (ascending squared L2), d_I i64[nq,k]; missing = (3.4028235e38,-1) */
+int rvcb_index_search(rvcb_index* ix, const float* d_q, int nq, int k, float* d_D, int64_t* d_I, void* stream);
+/* feats_out = rate * sum_k w_k big_npy[I_k] + (1-rate) * feats_in,  w = (1/D)^2 normalised (pipeline.py:129-138) */
+int rvcb_index_blend(rvcb_index* ix, const float* d_feats_in, int nq, int k, const float* d_D, const int64_t* d_I,
+                     float index_rate, float* d_feats_out, void* stream);
+/* exact brute-force L2 top-1 over d_db f32[n,d] (BASELINE config #5) */
+int rvcb_knn_bruteforce_top1(const float* d_db, int64_t n, int d, const float* d_q, int nq, float* d_D,
+                             int64_t* d_I, void* stream);
+void rvcb_index_destroy(rvcb_index* ix);
+
+/* ---- retrieval epilogue: x2 nearest upsample + protect mix (pipeline.py:140-160) ----------- */
+/* d_feats f32[T_h,C], d_feats0 (nullable) f32[T_h,C], d_pitchf (nullable) f32[T]; out f32[T,C], T <= 2*T_h */
+int rvcb_upsample_protect(const float* d_feats, const float* d_feats0, int T_h, int C, const float* d_pitchf, int T,
+                          float protect, float* d_out, void* stream);
+
+/* ---- RMVPE f0 -------------------------------------------------------------------------------
+ * replaces: RMVPE.compute_f0 -> mel_extractor + _mel2hidden + _decode (rvc/f0/rmvpe.py:96-164). */
+int rvcb_rmvpe_create(const rvcb_weights* w, rvcb_rmvpe** out);
+int rvcb_rmvpe_num_frames(int n_samples);
+/* d_wav f32[n]; outputs (each nullable): d_mel f32[128, n_frames] log-mel, d_hidden f32[n_frames,360] salience,
+ * d_f0 f32[n_frames] decoded Hz (threshold thred, 0 = unvoiced) */
+int rvcb_rmvpe_infer(rvcb_rmvpe* h, const float* d_wav, int n_samples, float thred, float* d_mel, float* d_hidden,
+                     float* d_f0, int* n_frames, void* stream);
+void rvcb_rmvpe_destroy(rvcb_rmvpe* h);
+
+/* ---- synthesizer ----------------------------------------------------------------------------
+ * replaces: SynthesizerTrnMsNSFsid.infer (rvc/layers/synthesizers.py:159-203). */
+typedef struct rvcb_synth_config {
+    int inter_channels, hidden_channels, filter_channels, n_heads, n_layers, kernel_size;
+    int n_resblock_kernels;  int resblock_kernel_sizes[4];  int resblock_dilations[4][3];
+    int n_upsamples;         int upsample_rates[4];         int upsample_kernel_sizes[4];
+    int upsample_initial_channel, spk_embed_dim, gin_channels, sr, encoder_dim;
+} rvcb_synth_config;
+int rvcb_synth_create(const rvcb_synth_config* cfg, const rvcb_weights* w, rvcb_synth** out);
+/* d_phone f32[T,encoder_dim]; d_pitch i64[T] (1..255); d_pitchf f32[T] Hz;
+ * d_noise_prior f32[inter, T - flow_head] (channel-major, like randn_like(m_p)); d_noise_src f32[T_dec*upp];
+ * skip_head/return_length/return_length2 < 0 mean "None".  d_wav_out f32[T_out*upp]; n_out receives T_out*upp. */
+int rvcb_synth_infer(rvcb_synth* h, const float* d_phone, int T, int sid, const int64_t* d_pitch, const float* d_pitchf,
+                     const float* d_noise_prior, const float* d_noise_src, int skip_head, int return_length,
+                     int return_length2, float* d_wav_out, int* n_out, void* stream);
+void rvcb_synth_destroy(rvcb_synth* h);
+
+/* ---- op-level entry for the unit tests: the implicit-GEMM engine -------------------------- */
+typedef struct rvcb_gemm_seg { int row_off, col_off, dw, nk; } rvcb_gemm_seg;
+typedef struct rvcb_gemm_desc {
+    const void* A; int64_t lda; int a_rows, a_cols, conv2d_W;
+    const void* B; int64_t ldb; int b_rows, b_cols;
+    int M, N, block_k, nseg;
+    int batch; int64_t a_row_z, a_col_z, b_row_z, b_col_z, c_z, bias_z; int b_col0;
+    const float* bias; int bias_per_row;
+    const float* res1; int64_t ldres1; const float* res2; int64_t ldres2;
+    float alpha; int act1; float act1_p; int act2; float act2_p; int gate;
+    float* out32; int64_t ld32; void* out16; int64_t ld16; int up2_C;
+    rvcb_gemm_seg seg[128];
+} rvcb_gemm_desc;
+/* impl: 0 = tcgen05/TMA kernel (product), 1 = SIMT restatement (validation only) */
+int rvcb_op_gemm(const rvcb_gemm_desc* d, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVCB200_H */

@@ -1,0 +1,53 @@
+// C ABI: runtime + op-level entry points (see include/rvcb200.h).
+#include "../../include/rvcb200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <cstring>
+
+namespace rvcb {
+unsigned long long g_launch_count = 0;
+static thread_local std::string g_err;
+void set_last_error(const std::string& s) { g_err = s; }
+}  // namespace rvcb
+
+#include "api_macros.h"
+
+extern "C" {
+
+const char* rvcb_last_error(void) { return rvcb::g_err.c_str(); }
+unsigned long long rvcb_launch_count(void) { return rvcb::g_launch_count; }
+const char* rvcb_version(void) { return "rvcb200 0.1 (sm_100a)"; }
+
+int rvcb_init(int device) {
+    RVCB_API_BEGIN
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    RVCB_CHECK(n > 0 && device < n, "no CUDA device " + std::to_string(device));
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    RVCB_CHECK(prop.major == 10, std::string("librvcb200 is built for sm_100a only; device is sm_") +
+                                     std::to_string(prop.major) + std::to_string(prop.minor));
+    RVCB_API_END
+}
+
+int rvcb_op_gemm(const rvcb_gemm_desc* d, int impl, void* stream) {
+    RVCB_API_BEGIN
+    rvcb::GemmArgs g;
+    g.A = (const __half*)d->A; g.lda = d->lda; g.a_rows = d->a_rows; g.a_cols = d->a_cols; g.conv2d_W = d->conv2d_W;
+    g.B = (const __half*)d->B; g.ldb = d->ldb; g.b_rows = d->b_rows; g.b_cols = d->b_cols;
+    g.M = d->M; g.N = d->N; g.block_k = d->block_k; g.nseg = d->nseg;
+    RVCB_CHECK(d->nseg > 0 && d->nseg <= rvcb::GEMM_MAX_SEG, "bad nseg");
+    for (int i = 0; i < d->nseg; ++i) g.seg[i] = {d->seg[i].row_off, d->seg[i].col_off, d->seg[i].dw, d->seg[i].nk};
+    g.batch = d->batch; g.a_row_z = d->a_row_z; g.a_col_z = d->a_col_z; g.b_row_z = d->b_row_z; g.b_col_z = d->b_col_z;
+    g.c_z = d->c_z; g.bias_z = d->bias_z; g.b_col0 = d->b_col0;
+    g.bias = d->bias; g.bias_per_row = d->bias_per_row; g.res1 = d->res1; g.ldres1 = d->ldres1; g.res2 = d->res2; g.ldres2 = d->ldres2;
+    g.alpha = d->alpha; g.act1 = d->act1; g.act1_p = d->act1_p; g.act2 = d->act2; g.act2_p = d->act2_p; g.gate = d->gate;
+    g.out32 = d->out32; g.ld32 = d->ld32; g.out16 = (__half*)d->out16; g.ld16 = d->ld16; g.up2_C = d->up2_C;
+    if (impl == 1) rvcb::gemm_simt(g, (cudaStream_t)stream);
+    else rvcb::gemm_tc(g, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Common host/device helpers for librvcb200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+namespace rvcb {
+
+void set_last_error(const std::string& s);
+
+struct Error : std::runtime_error {
+    explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define RVCB_CHECK(cond, msg)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            throw ::rvcb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) +      \
+                                ": " + (msg));                                                \
+        }                                                                                     \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            throw ::rvcb::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) +      \
+                                ": CUDA error: " + cudaGetErrorString(_e) + " in " #expr);    \
+        }                                                                                     \
+    } while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+// launch counter (bench.py reports gpu_launches from it)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+enum Act : int {
+    ACT_NONE = 0,
+    ACT_RELU = 1,
+    ACT_GELU = 2,      // exact erf
+    ACT_LRELU = 3,     // slope = act param
+    ACT_TANH = 4,
+    ACT_SIGMOID = 5,
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float p) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        case ACT_LRELU: return v > 0.f ? v : v * p;
+        case ACT_TANH: return tanhf(v);
+        case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// ---------------------------------------------------------------------------------------
+// Device bump arena: every handle owns one; activations of one forward pass are carved
+// from it and the pointer is reset at the start of each call (no cudaMalloc on the path).
+// ---------------------------------------------------------------------------------------
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0, high = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (base) CUDA_CHECK(cudaFree(base));
+        CUDA_CHECK(cudaMalloc(&base, bytes));
+        cap = bytes;
+    }
+    void reset() { off = 0; }
+    template <typename T>
+    T* alloc(size_t n) {
+        size_t bytes = (n * sizeof(T) + 1023) & ~size_t(1023);
+        RVCB_CHECK(off + bytes <= cap, "arena overflow: need " + std::to_string(off + bytes) + " have " + std::to_string(cap));
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        if (off > high) high = off;
+        return p;
+    }
+    ~Arena() {
+        if (base) cudaFree(base);
+    }
+};
+
+template <typename T>
+T* dev_upload(const T* host, size_t n) {
+    T* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, n * sizeof(T)));
+    CUDA_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+}  // namespace rvcb

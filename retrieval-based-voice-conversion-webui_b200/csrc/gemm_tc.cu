@@ -1,0 +1,558 @@
+// tcgen05 + TMA implicit-GEMM kernel for sm_100a (see gemm.cuh for the contract).
+//
+// Persistent, warp-specialised CTA of 192 threads, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring, mbarrier tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
+//                               tcgen05.commit releases smem slots / publishes the accumulator)
+//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused bias/act/residual -> global)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// Conv taps are K-segments whose A tile is the same matrix at a shifted TMA coordinate;
+// zero padding comes from TMA out-of-bounds fill, so no im2col buffer ever exists.
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace rvcb {
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct SegPacked {
+    short row, col, nk;
+    signed char dw, pad;
+};
+
+struct KParams {
+    int M, N, nseg, batch, num_m_tiles, num_n_tiles, num_tiles, total_kb;
+    int conv2d_W, BH;
+    int a_row_z, a_col_z, b_row_z, b_col_z, b_col0;
+    long c_z, bias_z;
+    const float* bias;
+    int bias_per_row;
+    const float* res1; long ldres1;
+    const float* res2; long ldres2;
+    float alpha;
+    int act1; float act1_p;
+    int act2; float act2_p;
+    int gate;
+    float* out32; long ld32;
+    __half* out16; long ld16;
+    int up2_C;
+    int vec_ok;
+    SegPacked seg[GEMM_MAX_SEG];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100).
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout type
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = (BK == 64) ? 2ull : (BK == 32) ? 4ull : 6ull;     // SW128 / SW64 / SW32
+    constexpr uint64_t sbo = (8 * BK * 2) >> 4;                                  // 8 rows of BK fp16
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 192;
+constexpr int BM = 128;
+
+template <int BN, int BK>
+struct Cfg {
+    static constexpr int A_STAGE = BM * BK * 2;
+    static constexpr int B_STAGE_RAW = BN * BK * 2;
+    static constexpr int B_STAGE = (B_STAGE_RAW + 1023) / 1024 * 1024;
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    static constexpr int STAGES = (196608 / STAGE) > 8 ? 8 : (196608 / STAGE);
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t TX_BYTES = A_STAGE + B_STAGE_RAW;
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ KParams p) {
+    using C = Cfg<BN, BK>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::STAGES * C::A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint64_t* full_bar = bars;                      // [STAGES]
+    uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * C::STAGES;     // [2]
+    uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_z = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_z;
+                const int rem = tile - z * tiles_per_z;
+                const int mt = rem / p.num_n_tiles;
+                const int nt = rem - mt * p.num_n_tiles;
+                int kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const SegPacked sg = p.seg[s];
+                    for (int kc = 0; kc < sg.nk; ++kc, ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
+                        const int ac0 = z * p.a_col_z + sg.col + kc * BK;
+                        if (p.conv2d_W == 0) {
+                            tma_load_3d(smem_a + stage * C::A_STAGE, &tmap_a, &full_bar[stage], ac0,
+                                        mt * BM + sg.row + z * p.a_row_z, 0);
+                        } else {
+                            tma_load_3d(smem_a + stage * C::A_STAGE, &tmap_a, &full_bar[stage], ac0, (int)sg.dw,
+                                        mt * p.BH + sg.row);
+                        }
+                        tma_load_2d(smem_b + stage * C::B_STAGE, &tmap_b, &full_bar[stage],
+                                    p.b_col0 + z * p.b_col_z + kb * BK, nt * BN + z * p.b_row_z);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.total_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + stage * C::A_STAGE);
+                    const uint32_t b_addr = smem_u32(smem_b + stage * C::B_STAGE);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
+                        const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
+                        umma_f16(tmem_c, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);           // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int z = tile / tiles_per_z;
+            const int rem = tile - z * tiles_per_z;
+            const int mt = rem / p.num_n_tiles;
+            const int nt = rem - mt * p.num_n_tiles;
+            const int m = mt * BM + row_in_tile;
+            const bool row_ok = m < p.M;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+
+            // output row base (elements) for this thread
+            long orow;        // row index into the output matrices
+            if (p.up2_C == 0) {
+                orow = m;
+            } else {
+                orow = 0;     // computed per column group below
+            }
+            const float* r1 = p.res1 ? p.res1 + z * p.c_z + (long)m * p.ldres1 : nullptr;
+            const float* r2 = p.res2 ? p.res2 + z * p.c_z + (long)m * p.ldres2 : nullptr;
+            const float bias_row = (p.bias && p.bias_per_row && row_ok) ? p.bias[m] : 0.f;
+            const float* biasz = p.bias ? p.bias + z * p.bias_z : nullptr;
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 16; ++c) {
+                uint32_t raw[16];
+                tmem_ld16(taddr + c * 16, raw);
+                tmem_ld_wait();
+                const int n0 = nt * BN + c * 16;
+                if (row_ok && n0 < p.N) {
+                    float v[16];
+                    const bool full = (n0 + 16 <= p.N);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (p.bias) {
+                        if (p.bias_per_row) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += bias_row;
+                        } else if (full) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(biasz + n0 + i);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + i < p.N) v[i] += biasz[n0 + i];
+                        }
+                    }
+                    if (r1) {
+                        if (full && p.vec_ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(r1 + n0 + i);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n0 + i < p.N) v[i] += r1[n0 + i];
+                        }
+                    }
+                    if (p.gate) {
+                        // (tanh, sigmoid) column pairs -> N/2 outputs
+                        const int o0 = n0 >> 1;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (n0 + 2 * i + 1 < p.N) {
+                                const float g = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
+                                if (p.out32) p.out32[z * p.c_z + (long)m * p.ld32 + o0 + i] = g;
+                                if (p.out16) p.out16[z * p.c_z + (long)m * p.ld16 + o0 + i] = __float2half_rn(g);
+                            }
+                        }
+                    } else {
+                        if (p.act1 != ACT_NONE) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act1, p.act1_p);
+                        }
+                        if (p.alpha != 1.f) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+                        }
+                        if (r2) {
+                            if (full && p.vec_ok) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 b = *reinterpret_cast<const float4*>(r2 + n0 + i);
+                                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (n0 + i < p.N) v[i] += r2[n0 + i];
+                            }
+                        }
+                        long ocol = n0;
+                        if (p.up2_C) {
+                            // n = (a*2+b)*C + co ; input pixel m = i*W + j -> output pixel (2i+a, 2j+b)
+                            const int W = p.conv2d_W, Cc = p.up2_C;
+                            const int ab = n0 / Cc, co = n0 - ab * Cc;
+                            const int ii = m / W, jj = m - ii * W;
+                            orow = (long)(2 * ii + (ab >> 1)) * (2 * W) + 2 * jj + (ab & 1);
+                            ocol = co;
+                        }
+                        if (p.out32) {
+                            float* o = p.out32 + z * p.c_z + orow * p.ld32 + ocol;
+                            if (full && p.vec_ok) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4)
+                                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (n0 + i < p.N) o[i] = v[i];
+                            }
+                        }
+                        if (p.out16) {
+                            __half* o = p.out16 + z * p.c_z + orow * p.ld16 + ocol;
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __half2 h2 = __floats2half2_rn(apply_act(v[2 * i], p.act2, p.act2_p),
+                                                                     apply_act(v[2 * i + 1], p.act2, p.act2_p));
+                                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            if (full && p.vec_ok) {
+                                *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (n0 + i < p.N)
+                                        o[i] = __ushort_as_half((unsigned short)((pk[i >> 1] >> ((i & 1) * 16)) & 0xFFFF));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    });
+    RVCB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int bk) {
+    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static void encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box, int bk) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    RVCB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    for (int i = 0; i < rank - 1; ++i) RVCB_CHECK(strides_bytes[i] % 16 == 0, "TMA stride must be a multiple of 16 bytes");
+    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+template <int BN, int BK>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& p, cudaStream_t stream) {
+    using C = Cfg<BN, BK>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    gemm_tc_kernel<BN, BK><<<grid, kThreads, C::SMEM, stream>>>(ta, tb, p);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+static int pick_bn(int N) {
+    if (N <= 16) return 16;
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    return 128;
+}
+
+void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
+    RVCB_CHECK(g.A && g.B && g.M > 0 && g.N > 0 && g.nseg > 0 && g.nseg <= GEMM_MAX_SEG, "gemm: bad arguments");
+    RVCB_CHECK(g.block_k == 64 || g.block_k == 32 || g.block_k == 16, "gemm: block_k must be 16/32/64");
+    RVCB_CHECK(g.out32 || g.out16, "gemm: no output");
+    const int BK = g.block_k;
+    int BN = pick_bn(g.N);
+    if (BK == 32 && BN > 64) BN = 64;
+    if (BK == 16 && BN > 32) BN = 32;
+
+    KParams p{};
+    p.M = g.M; p.N = g.N; p.nseg = g.nseg; p.batch = g.batch;
+    p.num_m_tiles = ceil_div(g.M, BM);
+    p.num_n_tiles = ceil_div(g.N, BN);
+    p.num_tiles = p.num_m_tiles * p.num_n_tiles * g.batch;
+    p.total_kb = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+        p.seg[s].row = (short)g.seg[s].row_off;
+        p.seg[s].col = (short)g.seg[s].col_off;
+        p.seg[s].nk = (short)g.seg[s].nk;
+        p.seg[s].dw = (signed char)g.seg[s].dw;
+        p.total_kb += g.seg[s].nk;
+    }
+    RVCB_CHECK(p.total_kb > 0, "gemm: empty K");
+    p.conv2d_W = g.conv2d_W;
+    p.BH = g.conv2d_W ? BM / g.conv2d_W : 0;
+    p.a_row_z = (int)g.a_row_z; p.a_col_z = (int)g.a_col_z; p.b_row_z = (int)g.b_row_z; p.b_col_z = (int)g.b_col_z;
+    p.b_col0 = g.b_col0;
+    p.c_z = g.c_z; p.bias_z = g.bias_z;
+    p.bias = g.bias; p.bias_per_row = g.bias_per_row;
+    p.res1 = g.res1; p.ldres1 = g.ldres1; p.res2 = g.res2; p.ldres2 = g.ldres2;
+    p.alpha = g.alpha; p.act1 = g.act1; p.act1_p = g.act1_p; p.act2 = g.act2; p.act2_p = g.act2_p;
+    p.gate = g.gate;
+    p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
+    p.up2_C = g.up2_C;
+    auto al = [](const void* ptr, int a) { return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % a) == 0; };
+    bool v = al(g.out32, 16) && al(g.out16, 16) && al(g.res1, 16) && al(g.res2, 16) && al(g.bias, 16);
+    if (g.out32) v = v && (g.ld32 % 4 == 0);
+    if (g.out16) v = v && (g.ld16 % 8 == 0);
+    if (g.res1) v = v && (g.ldres1 % 4 == 0);
+    if (g.res2) v = v && (g.ldres2 % 4 == 0);
+    v = v && (g.c_z % 8 == 0) && (g.bias_z % 4 == 0);
+    if (g.up2_C) v = v && (g.up2_C % 16 == 0);
+    p.vec_ok = v ? 1 : 0;
+    if (g.bias && !g.bias_per_row) RVCB_CHECK(al(g.bias, 16) && g.bias_z % 4 == 0, "gemm: bias must be 16B aligned");
+
+    // ---- tensor maps ----
+    CUtensorMap ta, tb;
+    if (g.conv2d_W == 0) {
+        cuuint64_t dims[3] = {(cuuint64_t)g.a_cols, (cuuint64_t)g.a_rows, 1};
+        cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.lda * 2 * (cuuint64_t)g.a_rows};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+        encode_map(&ta, g.A, 3, dims, str, box, BK);
+    } else {
+        const int W = g.conv2d_W;
+        RVCB_CHECK(W >= 1 && W <= 128 && (BM % W) == 0, "gemm: conv2d W must divide 128");
+        cuuint64_t dims[3] = {(cuuint64_t)g.a_cols, (cuuint64_t)W, (cuuint64_t)g.a_rows};
+        cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.lda * 2 * (cuuint64_t)W};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)(BM / W)};
+        encode_map(&ta, g.A, 3, dims, str, box, BK);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.b_cols, (cuuint64_t)g.b_rows};
+        cuuint64_t str[1] = {(cuuint64_t)g.ldb * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        encode_map(&tb, g.B, 2, dims, str, box, BK);
+    }
+
+#define RVCB_LAUNCH(bn, bk)                          \
+    if (BN == bn && BK == bk) {                      \
+        launch<bn, bk>(ta, tb, p, stream);           \
+        return;                                      \
+    }
+    RVCB_LAUNCH(16, 64) RVCB_LAUNCH(32, 64) RVCB_LAUNCH(64, 64) RVCB_LAUNCH(128, 64)
+    RVCB_LAUNCH(16, 32) RVCB_LAUNCH(32, 32) RVCB_LAUNCH(64, 32)
+    RVCB_LAUNCH(16, 16) RVCB_LAUNCH(32, 16)
+#undef RVCB_LAUNCH
+    RVCB_CHECK(false, "gemm: no kernel instance");
+}
+
+}  // namespace rvcb
