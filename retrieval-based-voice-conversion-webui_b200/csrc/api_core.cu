@@ -51,3 +51,37 @@ int rvcb_op_gemm(const rvcb_gemm_desc* d, int impl, void* stream) {
 }
 
 }  // extern "C"
+
+// ---- weight container ----------------------------------------------------------------------
+#include "weights.cuh"
+extern "C" {
+int rvcb_weights_create(rvcb_weights** out) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(out, "null argument");
+    *out = new rvcb_weights();
+    RVCB_API_END
+}
+int rvcb_weights_add(rvcb_weights* w, const char* name, const float* host_data, int ndim, const int64_t* shape) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(w && name && (host_data || ndim == 0), "null argument");
+    rvcb_weights::Tensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        t.shape.push_back(shape[i]);
+        n *= shape[i];
+    }
+    t.data.assign(host_data, host_data + n);
+    w->t[std::string(name)] = std::move(t);
+    RVCB_API_END
+}
+void rvcb_weights_destroy(rvcb_weights* w) { delete w; }
+}
+
+#include "kernels.cuh"
+extern "C" int rvcb_upsample_protect(const float* d_feats, const float* d_feats0, int T_h, int C, const float* d_pitchf, int T,
+                                     float protect, float* d_out, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_feats && d_out, "null argument");
+    rvcb::upsample_protect(d_feats, d_feats0, T_h, C, d_pitchf, T, protect, d_out, (cudaStream_t)stream);
+    RVCB_API_END
+}

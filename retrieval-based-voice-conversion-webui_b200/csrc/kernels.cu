@@ -1,0 +1,447 @@
+// SIMT kernels around the implicit-GEMM engine.  All fp32 math; no fast-math.
+#include "kernels.cuh"
+
+namespace rvcb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, long ldx, int rows, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, float* out32, long ld32, __half* out16, long ld16) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (long)row * ldx;
+    float v[32];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        v[i] = c < C ? xr[c] : 0.f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        const float d = c < C ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) {
+            const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            if (out32) out32[(long)row * ld32 + c] = y;
+            if (out16) out16[(long)row * ld16 + c] = __float2half_rn(y);
+        }
+    }
+}
+
+void layernorm_rows(const float* x, long ldx, int rows, int C, const float* gamma, const float* beta, float eps, float* out32,
+                    long ld32, __half* out16, long ld16, cudaStream_t s) {
+    RVCB_CHECK(C <= 1024, "layernorm: C too large");
+    layernorm_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, ldx, rows, C, gamma, beta, eps, out32, ld32, out16, ld16);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// HuBERT conv0 + GroupNorm(512 groups of 1 channel, over time) + GELU
+// ---------------------------------------------------------------------------------------------
+constexpr int C0_TSTEP = 32;
+__global__ void hubert_conv0_kernel(const float* __restrict__ wav, int n_samples, const float* __restrict__ w, float* __restrict__ y,
+                                    double* __restrict__ stats, int T0) {
+    __shared__ float xs[C0_TSTEP * 5 + 8];
+    const int c = threadIdx.x;                 // 512 threads = channels
+    const int t0 = blockIdx.x * C0_TSTEP;
+    for (int i = threadIdx.x; i < C0_TSTEP * 5 + 5; i += blockDim.x) {
+        const long g = (long)t0 * 5 + i;
+        xs[i] = g < n_samples ? wav[g] : 0.f;
+    }
+    float wr[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) wr[j] = w[c * 10 + j];
+    __syncthreads();
+    float s1 = 0.f, s2 = 0.f;
+    for (int tt = 0; tt < C0_TSTEP; ++tt) {
+        const int t = t0 + tt;
+        if (t >= T0) break;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc = fmaf(wr[j], xs[tt * 5 + j], acc);
+        y[(long)t * 512 + c] = acc;
+        s1 += acc;
+        s2 += acc * acc;
+    }
+    atomicAdd(&stats[c], (double)s1);
+    atomicAdd(&stats[512 + c], (double)s2);
+}
+
+__global__ void hubert_gn_gelu_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, __half* __restrict__ out, int T0) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)T0 * 512) return;
+    const int c = (int)(idx & 511);
+    const double mean = stats[c] / T0;
+    const double var = stats[512 + c] / T0 - mean * mean;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float v = (y[idx] - (float)mean) * rstd * gamma[c] + beta[c];
+    out[idx] = __float2half_rn(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));
+}
+
+void hubert_conv0_gn_gelu(const float* wav, int n_samples, const float* w, const float* gamma, const float* beta, float* scratch_y,
+                          double* scratch_stats, __half* out16, int T0, cudaStream_t s) {
+    CUDA_CHECK(cudaMemsetAsync(scratch_stats, 0, sizeof(double) * 1024, s));
+    hubert_conv0_kernel<<<ceil_div(T0, C0_TSTEP), 512, 0, s>>>(wav, n_samples, w, scratch_y, scratch_stats, T0);
+    KERNEL_CHECK();
+    const long n = (long)T0 * 512;
+    hubert_gn_gelu_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(scratch_y, scratch_stats, gamma, beta, out16, T0);
+    KERNEL_CHECK();
+    count_launch(2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// row softmax (+ relative-position band)
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_kernel(const float* __restrict__ S, long lds, int T, __half* __restrict__ P, long ldp,
+                               const float* __restrict__ qrel, long ldq, int win, __half* __restrict__ prel) {
+    extern __shared__ float row[];
+    __shared__ float red[32];
+    const long r = blockIdx.x;                  // h*T + i
+    const int i = (int)(r % T);
+    const float* sr = S + r * lds;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < T; j += blockDim.x) {
+        float v = sr[j];
+        if (qrel) {
+            const int d = j - i;
+            if (d >= -win && d <= win) v += qrel[r * ldq + d + win];
+        }
+        row[j] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        v = warp_max(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    mx = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < T; j += blockDim.x) {
+        const float e = expf(row[j] - mx);
+        row[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    const float inv = 1.f / red[0];
+    __half* pr = P + r * ldp;
+    for (int j = threadIdx.x; j < ldp; j += blockDim.x) pr[j] = __float2half_rn(j < T ? row[j] * inv : 0.f);
+    if (prel) {
+        for (int q = threadIdx.x; q < 64; q += blockDim.x) {
+            const int j = i + q - win;
+            prel[r * 64 + q] = __float2half_rn((q <= 2 * win && j >= 0 && j < T) ? row[j] * inv : 0.f);
+        }
+    }
+}
+
+void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, const float* qrel, long ldq, int win, __half* prel,
+                  cudaStream_t s) {
+    RVCB_CHECK((size_t)T * 4 <= 48 * 1024, "softmax: row too long");
+    softmax_kernel<<<H * T, 256, T * sizeof(float), s>>>(S, lds, T, P, ldp, qrel, ldq, win, prel);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2half_rn(x[i]);
+}
+void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s) {
+    cast_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(x, y, n);
+    KERNEL_CHECK();
+    count_launch();
+}
+__global__ void half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __half2float(x[i]);
+}
+void half_to_float(const __half* x, float* y, long n, cudaStream_t s) {
+    half_to_float_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(x, y, n);
+    KERNEL_CHECK();
+    count_launch();
+}
+__global__ void cast2d_kernel(const float* __restrict__ x, long ldx, __half* __restrict__ y, long ldy, int rows, int cols) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows * cols) return;
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    y[r * ldy + c] = __float2half_rn(x[r * ldx + c]);
+}
+void cast_f32_f16_2d(const float* x, long ldx, __half* y, long ldy, int rows, int cols, cudaStream_t s) {
+    cast2d_kernel<<<(unsigned)ceil_div_l((long)rows * cols, 256), 256, 0, s>>>(x, ldx, y, ldy, rows, cols);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ x, const float* __restrict__ b,
+                              const float* __restrict__ add, float* __restrict__ y, int N, int K) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(W[(long)n * K + k], x[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[n] = acc + (b ? b[n] : 0.f) + (add ? add[n] : 0.f);
+}
+void matvec(const float* W, const float* x, const float* b, const float* add, float* y, int N, int K, cudaStream_t s) {
+    matvec_kernel<<<ceil_div(N, 8), 256, 0, s>>>(W, x, b, add, y, N, K);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void textenc_embed_kernel(const float* __restrict__ lin, const long long* __restrict__ pitch, const float* __restrict__ emb,
+                                     int T, int C, float scale, float* __restrict__ o32, __half* __restrict__ o16) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    float v = lin[i];
+    if (pitch) v += emb[(long)pitch[t] * C + c];
+    v *= scale;
+    v = v > 0.f ? v : v * 0.1f;
+    o32[i] = v;
+    o16[i] = __float2half_rn(v);
+}
+void textenc_embed(const float* lin, const long long* pitch, const float* emb_pitch, int T, int C, float scale, float* out32,
+                   __half* out16, cudaStream_t s) {
+    textenc_embed_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(lin, pitch, emb_pitch, T, C, scale, out32, out16);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void prior_kernel(const float* __restrict__ stats, const float* __restrict__ noise, long ldn, int T, int C, float* __restrict__ z) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    const float m = stats[(long)t * 2 * C + c], logs = stats[(long)t * 2 * C + C + c];
+    z[i] = m + expf(logs) * noise[(long)c * ldn + t] * 0.66666f;
+}
+void prior_sample(const float* stats, const float* noise, long ldn, int T, int C, float* z, cudaStream_t s) {
+    prior_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(stats, noise, ldn, T, C, z);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void flip_kernel(const float* __restrict__ in, float* __restrict__ out, __half* __restrict__ x0, int T, int C, int hc) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    const float v = in[(long)t * C + (C - 1 - c)];
+    out[i] = v;
+    if (c < hc) x0[(long)t * hc + c] = __float2half_rn(v);
+}
+void flip_channels(const float* in, float* out, __half* x0_16, int T, int C, int half_c, cudaStream_t s) {
+    flip_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(in, out, x0_16, T, C, half_c);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void add_rowvec_kernel(float* __restrict__ x, const float* __restrict__ v, int T, int C, __half* __restrict__ o16, float slope) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const int c = (int)(i % C);
+    const float y = x[i] + v[c];
+    x[i] = y;
+    if (o16) o16[i] = __float2half_rn(y > 0.f ? y : y * slope);
+}
+void add_rowvec(float* x, const float* v, int T, int C, __half* out16, float lrelu_slope, cudaStream_t s) {
+    add_rowvec_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(x, v, T, C, out16, lrelu_slope);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// NSF sine source
+// ---------------------------------------------------------------------------------------------
+__global__ void sine_phase_kernel(const float* __restrict__ f0, int T, int upp, float sr, float* __restrict__ phase) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double acc = 0.0;                 // torch's CPU cumsum accumulates float in double (acc_type<float,false>)
+    phase[0] = 0.f;
+    const float a_last = (float)upp;
+    for (int t = 0; t + 1 < T; ++t) {
+        const float rad = __fmul_rn(__fdiv_rn(f0[t], sr), a_last);
+        const float r2 = fmodf(__fadd_rn(rad, 0.5f), 1.0f) - 0.5f;
+        acc += (double)r2;
+        phase[t + 1] = fmodf((float)acc, 1.0f);
+    }
+}
+__global__ void sine_wave_kernel(const float* __restrict__ f0, const float* __restrict__ phase, int T, int upp, float sr,
+                                 const float* __restrict__ noise, float lw, float lb, float* __restrict__ har) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * upp) return;
+    const int t = (int)(i / upp), j = (int)(i - (long)t * upp);
+    const float f = f0[t];
+    float rad = __fmul_rn(__fdiv_rn(f, sr), (float)(j + 1));
+    rad = __fadd_rn(rad, phase[t]);
+    const float sine = __fmul_rn(sinf(__fmul_rn(6.283185307179586f, rad)), 0.1f);
+    const float uv = f > 0.f ? 1.f : 0.f;
+    const float namp = __fadd_rn(__fmul_rn(uv, 0.003f), __fdiv_rn(__fmul_rn(1.f - uv, 0.1f), 3.f));
+    const float sw = __fadd_rn(__fmul_rn(sine, uv), __fmul_rn(namp, noise[i]));
+    har[i] = tanhf(__fadd_rn(__fmul_rn(sw, lw), lb));
+}
+void sine_source(const float* f0, int T, int upp, int sr, const float* noise, float lin_w, float lin_b, float* phase_scratch,
+                 float* har, cudaStream_t s) {
+    sine_phase_kernel<<<1, 32, 0, s>>>(f0, T, upp, (float)sr, phase_scratch);
+    KERNEL_CHECK();
+    const long n = (long)T * upp;
+    sine_wave_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(f0, phase_scratch, T, upp, (float)sr, noise, lin_w, lin_b, har);
+    KERNEL_CHECK();
+    count_launch(2);
+}
+
+__global__ void noise_conv_kernel(float* __restrict__ x, __half* __restrict__ x16, const float* __restrict__ har, long n_har,
+                                  const float* __restrict__ w, const float* __restrict__ b, int T, int C, int k, int stride, int pad,
+                                  float slope) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const long t = i / C;
+    const int c = (int)(i - t * C);
+    float acc = b[c];
+    const long base = t * stride - pad;
+    for (int j = 0; j < k; ++j) {
+        const long q = base + j;
+        if (q >= 0 && q < n_har) acc = fmaf(har[q], w[c * k + j], acc);
+    }
+    const float y = x[i] + acc;
+    x[i] = y;
+    x16[i] = __float2half_rn(y > 0.f ? y : y * slope);
+}
+void noise_conv_add(float* x, __half* x16, const float* har, long n_har, const float* w, const float* b, int T, int C, int k,
+                    int stride, int pad, float slope, cudaStream_t s) {
+    noise_conv_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(x, x16, har, n_har, w, b, T, C, k, stride, pad, slope);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void interp_rows_kernel(const float* __restrict__ in, int T_in, float* __restrict__ out, int T_out, int C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T_out * C) return;
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    const float scale = (float)T_in / (float)T_out;
+    float src = ((float)t + 0.5f) * scale - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int i0 = (int)src;
+    if (i0 > T_in - 1) i0 = T_in - 1;
+    const int i1 = i0 + 1 < T_in ? i0 + 1 : i0;
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    out[i] = l0 * in[(long)i0 * C + c] + l1 * in[(long)i1 * C + c];
+}
+void interp_linear_rows(const float* in, int T_in, float* out, int T_out, int C, cudaStream_t s) {
+    interp_rows_kernel<<<(unsigned)ceil_div_l((long)T_out * C, 256), 256, 0, s>>>(in, T_in, out, T_out, C);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void upsample_protect_kernel(const float* __restrict__ f, const float* __restrict__ f0, int T_h, int C,
+                                        const float* __restrict__ pitchf, int T, float protect, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)T * C) return;
+    const int t = (int)(i / C), c = (int)(i - (long)t * C);
+    const int th = t >> 1;
+    float v = f[(long)th * C + c];
+    if (f0 != nullptr && pitchf != nullptr && protect < 0.5f) {
+        const float pf = pitchf[t];
+        float pm = pf > 0.f ? 1.f : pf;       // pitchff[pitchf > 0] = 1
+        if (pf < 1.f) pm = protect;           // pitchff[pitchf < 1] = protect
+        v = v * pm + f0[(long)th * C + c] * (1.f - pm);
+    }
+    out[i] = v;
+}
+void upsample_protect(const float* feats, const float* feats0, int T_h, int C, const float* pitchf, int T, float protect, float* out,
+                      cudaStream_t s) {
+    RVCB_CHECK(T <= 2 * T_h, "upsample_protect: T > 2*T_h");
+    upsample_protect_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(feats, feats0, T_h, C, pitchf, T, protect, out);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 SIMT GEMM, 64x64x16 tiles, 4x4 register blocking
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
+                                                       float* __restrict__ C, long ldc, int M, int N, int K) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    const int lk = threadIdx.x & 15, lr = threadIdx.x >> 4;     // loader: k index, row (0..15)
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lr + 16 * i;
+            const int k = k0 + lk;
+            As[lk][r] = (m0 + r < M && k < K) ? A[(long)(m0 + r) * lda + k] : 0.f;
+            Bs[lk][r] = (n0 + r < N && k < K) ? B[(long)(n0 + r) * ldb + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = As[k][ty * 4 + i];
+                b[i] = Bs[k][tx * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) C[(long)m * ldc + n] = acc[i][j];
+        }
+}
+void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, cudaStream_t s) {
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+    sgemm_nt_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+}  // namespace rvcb

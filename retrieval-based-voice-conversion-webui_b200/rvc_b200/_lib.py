@@ -89,10 +89,17 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU / PyTorch fallback for the hot path)")
         l = C.CDLL(LIB_PATH)
+        missing = []
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(l, name)          # AttributeError if the .so does not export a declared symbol
+            try:
+                fn = getattr(l, name)
+            except AttributeError:
+                missing.append(name)
+                continue
             fn.restype = res
             fn.argtypes = args
+        if missing and not os.environ.get("RVCB_ALLOW_PARTIAL_LIB"):
+            raise RuntimeError(f"{LIB_PATH} does not export: {missing} (stale build? run __graft_entry__.build())")
         _lib = l
     return _lib
 

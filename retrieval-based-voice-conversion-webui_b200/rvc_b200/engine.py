@@ -1,0 +1,257 @@
+"""Thin Python owners of the librvcb200 handles.  PyTorch is used only for device memory,
+streams and host<->device copies (plumbing); all arithmetic happens inside the C ABI calls."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk_dev(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class Weights:
+    """Host fp32 tensors keyed by the reference's state_dict names -> rvcb_weights handle."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor]):
+        _lib.lib()
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().rvcb_weights_create(C.byref(self.h)))
+        for k, v in state_dict.items():
+            if not torch.is_tensor(v) or not (v.is_floating_point()):
+                continue
+            a = np.ascontiguousarray(v.detach().cpu().float().numpy())
+            shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+            _lib.check(_lib.lib().rvcb_weights_add(self.h, k.encode(), a.ctypes.data_as(C.c_void_p), a.ndim, shape))
+
+    def close(self):
+        if self.h:
+            _lib.lib().rvcb_weights_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class Hubert:
+    """Replaces the fairseq HubertModel object for the calls the pipeline makes."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0):
+        _lib.init(device)
+        self.h = C.c_void_p()
+        with Weights(state_dict) as w:
+            _lib.check(_lib.lib().rvcb_hubert_create(w.h, C.byref(self.h)))
+        self.device = torch.device("cuda", device)
+
+    @staticmethod
+    def num_frames(n_samples: int) -> int:
+        return _lib.lib().rvcb_hubert_num_frames(n_samples)
+
+    def extract(self, wav: torch.Tensor, output_layer: int = 12) -> torch.Tensor:
+        """wav f32 [n] (device) -> f32 [T_h, 768] (device)"""
+        wav = _chk_dev(wav.reshape(-1), torch.float32, "wav")
+        T = self.num_frames(wav.numel())
+        if T < 1:
+            raise RuntimeError("hubert: input too short")
+        out = torch.empty(T, 768, device=wav.device, dtype=torch.float32)
+        nf = C.c_int(0)
+        _lib.check(_lib.lib().rvcb_hubert_extract_features(self.h, _p(wav), wav.numel(), output_layer, _p(out), C.byref(nf), _stream_ptr()))
+        return out
+
+    def final_proj(self, x: torch.Tensor) -> torch.Tensor:
+        x = _chk_dev(x.reshape(-1, 768), torch.float32, "x")
+        out = torch.empty(x.shape[0], 256, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().rvcb_hubert_final_proj(self.h, _p(x), x.shape[0], _p(out), _stream_ptr()))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_hubert_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Index:
+    """IVF-Flat index on the device; duck-types the faiss object the pipeline uses
+    (.search / .reconstruct_n / .ntotal) with device tensors in and out."""
+
+    def __init__(self, centroids: np.ndarray, vectors: np.ndarray, list_off: np.ndarray, list_ids: np.ndarray, device: int = 0):
+        _lib.init(device)
+        self.centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+        self.vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+        lo = np.ascontiguousarray(list_off, dtype=np.int64)
+        li = np.ascontiguousarray(list_ids, dtype=np.int64)
+        self.ntotal, self.d = self.vectors.shape
+        self.nlist = self.centroids.shape[0]
+        self.device = torch.device("cuda", device)
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().rvcb_index_create(self.centroids.ctypes.data_as(C.c_void_p), self.nlist,
+                                                self.vectors.ctypes.data_as(C.c_void_p), self.ntotal, self.d,
+                                                lo.ctypes.data_as(C.c_void_p), li.ctypes.data_as(C.c_void_p), C.byref(self.h)))
+
+    @classmethod
+    def from_oracle_layout(cls, idx, device: int = 0) -> "Index":
+        """idx: any object with .centroids, .vectors, .list_off, .list_ids (e.g. oracle.ivf.IVFFlat or the
+        .index reader)."""
+        return cls(idx.centroids, idx.vectors, idx.list_off, idx.list_ids, device)
+
+    def reconstruct_n(self, i0: int, n: int) -> np.ndarray:
+        return self.vectors[i0:i0 + n]
+
+    def search_device(self, q: torch.Tensor, k: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = _chk_dev(q.reshape(-1, self.d), torch.float32, "q")
+        D = torch.empty(q.shape[0], k, device=q.device, dtype=torch.float32)
+        I = torch.empty(q.shape[0], k, device=q.device, dtype=torch.int64)
+        _lib.check(_lib.lib().rvcb_index_search(self.h, _p(q), q.shape[0], k, _p(D), _p(I), _stream_ptr()))
+        return D, I
+
+    def search(self, x, k: int = 8):
+        """faiss-style: numpy in, numpy out (host buffers cross PCIe inside this call)."""
+        q = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+        D, I = self.search_device(q, k)
+        return D.cpu().numpy(), I.cpu().numpy()
+
+    def blend_device(self, feats: torch.Tensor, D: torch.Tensor, I: torch.Tensor, index_rate: float) -> torch.Tensor:
+        feats = _chk_dev(feats.reshape(-1, self.d), torch.float32, "feats")
+        out = torch.empty_like(feats)
+        _lib.check(_lib.lib().rvcb_index_blend(self.h, _p(feats), feats.shape[0], D.shape[1], _p(D), _p(I), float(index_rate), _p(out),
+                                               _stream_ptr()))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_index_destroy(self.h)
+        except Exception:
+            pass
+
+
+def knn_bruteforce_top1(db: torch.Tensor, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _lib.init(db.device.index or 0)
+    db = _chk_dev(db, torch.float32, "db")
+    q = _chk_dev(q, torch.float32, "q")
+    D = torch.empty(q.shape[0], device=q.device, dtype=torch.float32)
+    I = torch.empty(q.shape[0], device=q.device, dtype=torch.int64)
+    _lib.check(_lib.lib().rvcb_knn_bruteforce_top1(_p(db), db.shape[0], db.shape[1], _p(q), q.shape[0], _p(D), _p(I), _stream_ptr()))
+    return D, I
+
+
+def upsample_protect(feats: torch.Tensor, feats0: Optional[torch.Tensor], pitchf: Optional[torch.Tensor], T: int, protect: float) -> torch.Tensor:
+    feats = _chk_dev(feats, torch.float32, "feats")
+    T_h, Cc = feats.shape
+    out = torch.empty(T, Cc, device=feats.device, dtype=torch.float32)
+    f0 = None if feats0 is None else _chk_dev(feats0, torch.float32, "feats0")
+    pf = None if pitchf is None else _chk_dev(pitchf.reshape(-1), torch.float32, "pitchf")
+    _lib.check(_lib.lib().rvcb_upsample_protect(_p(feats), _p(f0), T_h, Cc, _p(pf), T, float(protect), _p(out), _stream_ptr()))
+    return out
+
+
+class Rmvpe:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0):
+        _lib.init(device)
+        self.h = C.c_void_p()
+        with Weights(state_dict) as w:
+            _lib.check(_lib.lib().rvcb_rmvpe_create(w.h, C.byref(self.h)))
+        self.device = torch.device("cuda", device)
+
+    @staticmethod
+    def num_frames(n_samples: int) -> int:
+        return _lib.lib().rvcb_rmvpe_num_frames(n_samples)
+
+    def infer(self, wav: torch.Tensor, thred: float = 0.03, want_mel: bool = False, want_hidden: bool = False):
+        wav = _chk_dev(wav.reshape(-1), torch.float32, "wav")
+        nf = self.num_frames(wav.numel())
+        mel = torch.empty(128, nf, device=wav.device) if want_mel else None
+        hid = torch.empty(nf, 360, device=wav.device) if want_hidden else None
+        f0 = torch.empty(nf, device=wav.device)
+        n = C.c_int(0)
+        _lib.check(_lib.lib().rvcb_rmvpe_infer(self.h, _p(wav), wav.numel(), float(thred), _p(mel), _p(hid), _p(f0), C.byref(n), _stream_ptr()))
+        return f0, mel, hid
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_rmvpe_destroy(self.h)
+        except Exception:
+            pass
+
+
+def synth_config_struct(config, encoder_dim: int) -> "_lib.SynthConfig":
+    (_spec, _seg, inter, hidden, filt, n_heads, n_layers, ksz, _pd, _rb, rb_k, rb_d, up_rates, up_init, up_k, n_spk, gin, sr) = config
+    if isinstance(sr, str):
+        sr = {"32k": 32000, "40k": 40000, "48k": 48000}[sr]
+    c = _lib.SynthConfig()
+    c.inter_channels, c.hidden_channels, c.filter_channels = inter, hidden, filt
+    c.n_heads, c.n_layers, c.kernel_size = n_heads, n_layers, ksz
+    c.n_resblock_kernels = len(rb_k)
+    for i, k in enumerate(rb_k):
+        c.resblock_kernel_sizes[i] = k
+        for j, d in enumerate(rb_d[i]):
+            c.resblock_dilations[i][j] = d
+    c.n_upsamples = len(up_rates)
+    for i, (u, k) in enumerate(zip(up_rates, up_k)):
+        c.upsample_rates[i] = u
+        c.upsample_kernel_sizes[i] = k
+    c.upsample_initial_channel, c.spk_embed_dim, c.gin_channels, c.sr, c.encoder_dim = up_init, n_spk, gin, sr, encoder_dim
+    return c
+
+
+class Synth:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config, encoder_dim: int = 768, device: int = 0):
+        _lib.init(device)
+        self.cfg = synth_config_struct(config, encoder_dim)
+        self.upp = 1
+        for i in range(self.cfg.n_upsamples):
+            self.upp *= self.cfg.upsample_rates[i]
+        self.inter = self.cfg.inter_channels
+        self.h = C.c_void_p()
+        with Weights(state_dict) as w:
+            _lib.check(_lib.lib().rvcb_synth_create(C.byref(self.cfg), w.h, C.byref(self.h)))
+        self.device = torch.device("cuda", device)
+
+    def infer(self, phone: torch.Tensor, sid: int, pitch: torch.Tensor, pitchf: torch.Tensor, noise_prior: torch.Tensor,
+              noise_src: torch.Tensor, skip_head: Optional[int] = None, return_length: Optional[int] = None,
+              return_length2: Optional[int] = None) -> torch.Tensor:
+        phone = _chk_dev(phone.reshape(-1, phone.shape[-1]), torch.float32, "phone")
+        T = phone.shape[0]
+        pitch = _chk_dev(pitch.reshape(-1), torch.int64, "pitch")
+        pitchf = _chk_dev(pitchf.reshape(-1), torch.float32, "pitchf")
+        noise_prior = _chk_dev(noise_prior.reshape(self.inter, -1), torch.float32, "noise_prior")
+        noise_src = _chk_dev(noise_src.reshape(-1), torch.float32, "noise_src")
+        T_dec = T if return_length is None else int(return_length)
+        T_out = T_dec if return_length2 is None else int(return_length2)
+        out = torch.empty(T_out * self.upp, device=phone.device, dtype=torch.float32)
+        n = C.c_int(0)
+        _lib.check(_lib.lib().rvcb_synth_infer(self.h, _p(phone), T, int(sid), _p(pitch), _p(pitchf), _p(noise_prior), _p(noise_src),
+                                               -1 if skip_head is None else int(skip_head),
+                                               -1 if return_length is None else int(return_length),
+                                               -1 if return_length2 is None else int(return_length2), _p(out), C.byref(n), _stream_ptr()))
+        return out[: n.value]
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_synth_destroy(self.h)
+        except Exception:
+            pass
