@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- RVC v2/48k inference hot path on B200 (BASELINE.json metric: 48 kHz output samples / s).
+
+One "step" = one 10 s / 16 kHz utterance through the whole path (config #2: v2/48k model, RMVPE f0,
+100k-vector IVF2564,Flat index, k=8, index_rate 0.75, x_pad=3 => 16 s of model compute, 479 040 output samples):
+HuBERT features -> IVF-Flat search + blend -> RMVPE f0 -> SynthesizerTrnMs768NSFsid.infer.
+
+  value   device-resident: audio_pad / pitch already in HBM, CUDA events around the kernels of one utterance
+  e2e     VC.vc_single (the reference's public entry) with HOST numpy audio in and host int16 audio out:
+          H2D / D2H copies, host DSP (filtfilt, reflect pad, f0 post-processing, RMS mix) inside the timed region
+  --impl reference   the reference's CPU path (oracle restatement, pinned against the reference's own modules)
+                     on the box's host cores for the same metric/config.
+Synthetic seeded weights / audio / index (no assets, no network): "data": "synthetic".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "retrieval-based-voice-conversion-webui_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+OUT_SAMPLES = 479040          # 160000 in @16k -> (2*799)*480 - 2*3*48000 out @48k
+UTT_SECONDS = 10.0
+ALGO_FLOPS = (246.0 + 117.1 + 1833.0) * 1e9     # BASELINE.md section 2, offline fp16-config column
+
+
+class Cfg:  # the object Pipeline reads (configs/config.py:219-230, fp16 "6G" preset)
+    x_pad, x_query, x_center, x_max, is_half = 3, 10, 60, 65, True
+
+    def __init__(self, device):
+        self.device = device
+        self.rmvpe_state_dict = None
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.maxmhz, self.stop_flag = gpu_index, [], set(), 0, False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(", ")
+                self.samples.append(float(o[0])); self.maxmhz = float(o[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), o[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.maxmhz or None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle restatement) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import ivf as OI, pipeline as OP, weights as OW
+    torch.set_num_threads(os.cpu_count())
+    cores = os.cpu_count()
+    audio = OW.synth_voice(UTT_SECONDS, seed=0).numpy()
+    vec = OW.index_vectors(100000, 768, 0).numpy()
+    idx = OI.build_ivf(vec, None, seed=0, exact_assign=False)
+    pipe = OP.OraclePipeline(48000, 3, 10, 60, 65, OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234), OW.V2_48K_CONFIG)
+    def step():
+        with torch.no_grad():
+            return pipe.pipeline(0, audio.copy(), 0, "rmvpe", idx, 0.75, 1, 48000, 0, 0.25, "v2", 0.33)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step()
+    dt = time.perf_counter() - t0
+    v = args.steps * OUT_SAMPLES / dt
+    line = {"impl": "reference", "metric": "48kHz audio samples/sec (v2/48k infer, RMVPE, IVF index)", "value": v, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "rtf_x": v / 48000.0,
+            "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)"},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x one full 10 s utterance (oracle pipeline, torch CPU fp32, all cores)"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    assert args.warmup >= 3 or os.environ.get("RVCB_BENCH_ALLOW_SHORT"), "timing hygiene: use --warmup >= 3"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rvc_b200 import _lib, synthetic as SY
+    from rvc_b200.engine import Index
+    from rvc_b200.index_build import build_ivf_layout
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    _lib.init(local_rank)
+
+    # ---- model containers (seeded synthetic checkpoints) ----
+    cfg = Cfg(str(dev))
+    cfg.rmvpe_state_dict = SY.rmvpe_weights(4321)
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(SY.hubert_weights(777), dev)
+    cpt = SY.synth_cpt(1234, "v2")
+    vc.get_vc(cpt)
+    # index: rank 0 builds the layout; the optional one-time broadcast over NCCL shares it (the only collective of the path)
+    if rank == 0:
+        lay = build_ivf_layout(SY.index_vectors(100000, 768, 0).numpy(), None, seed=0, device=str(dev))
+        blob = [lay.centroids, lay.vectors, lay.list_off, lay.list_ids]
+    if world > 1:
+        shapes = [None]
+        if rank == 0:
+            shapes = [[(b.shape, str(b.dtype)) for b in blob]]
+        dist.broadcast_object_list(shapes, src=0)
+        tens = []
+        for i, (shp, dt) in enumerate(shapes[0]):
+            t = torch.from_numpy(blob[i]).to(dev) if rank == 0 else torch.empty(shp, dtype=getattr(torch, dt.replace("float32", "float32")), device=dev)
+            dist.broadcast(t, src=0)
+            tens.append(t.cpu().numpy())
+        from rvc_b200.faiss_io import IVFLayout
+        lay = IVFLayout(*tens)
+    index = Index.from_oracle_layout(lay, local_rank)
+
+    audio = SY.synth_voice(UTT_SECONDS, seed=rank).numpy()          # each rank converts its own utterances (weak scaling)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def e2e_step():
+        info, out = vc.vc_single(0, audio, 0, None, "rmvpe", index, "", 0.75, 3, 0, 0.25, 0.33)
+        assert out is not None, info
+        return out[1]
+
+    # ---- device-resident step: same kernels, inputs already in HBM ----
+    from scipy import signal
+    from infer.modules.vc.pipeline import bh, ah
+    a = signal.filtfilt(bh, ah, np.divide(audio, max(1.0, np.abs(audio).max() / 0.95)))
+    audio_pad = torch.from_numpy(np.pad(a, (48000, 48000), mode="reflect").astype(np.float32)).to(dev)
+    p_len = audio_pad.shape[0] // 160
+    pitch_np, pitchf_np = vc.pipeline.f0_gen.calculate(audio_pad, p_len, 0, "rmvpe", 3)
+    hub, rmv, net = vc.hubert_model._m, vc.pipeline.f0_gen._rmvpe(), vc.net_g._synth
+    T2 = 2 * hub.num_frames(audio_pad.shape[0])
+    pitch = torch.tensor(pitch_np[:T2], device=dev).long()
+    pitchf = torch.tensor(pitchf_np[:T2].astype(np.float32), device=dev)
+    n1 = torch.randn(192, T2, device=dev)
+    n2 = torch.randn(T2 * 480, device=dev)
+    from rvc_b200 import engine
+
+    def dev_step():
+        f0, _, _ = rmv.infer(audio_pad, 0.03)
+        feats = hub.extract(audio_pad, 12)
+        D, I = index.search_device(feats, 8)
+        fb = index.blend_device(feats, D, I, 0.75)
+        phone = engine.upsample_protect(fb, feats, pitchf, T2, 0.33)
+        return net.infer(phone, 0, pitch, pitchf, n1, n2)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            flush.fill_(1)                      # L2 flush between timed iterations (outside the event pair)
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.lib().rvcb_launch_count()
+    dev_ms = timed(dev_step, args.steps, args.warmup)
+    launches = (_lib.lib().rvcb_launch_count() - l0) // (args.steps + args.warmup)
+    e2e_ms = timed(e2e_step, args.steps, args.warmup)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel family (gemm_tc): live CUDA events around every launch of one step set ----
+    import ctypes as C
+    _lib.check(_lib.lib().rvcb_prof_begin())
+    for _ in range(3):
+        dev_step()
+    gms, gn = C.c_double(0), C.c_ulonglong(0)
+    _lib.check(_lib.lib().rvcb_prof_end(C.byref(gms), C.byref(gn)))
+    gemm_ms_per_step = gms.value / 3
+    pk, pk_src = peaks()
+    achieved = ALGO_FLOPS / (gemm_ms_per_step * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+
+    value = world * args.steps * OUT_SAMPLES / (dev_ms * 1e-3)
+    e2e_v = world * args.steps * OUT_SAMPLES / (e2e_ms * 1e-3)
+    line = {
+        "metric": "48kHz audio samples/sec (v2/48k infer, RMVPE, IVF index)", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate+residuals",
+        "data": "synthetic", "rtf_x_per_gpu": value / world / 48000.0,
+        "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)",
+                   "l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1},
+        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(audio.nbytes * 256000 / 160000 + 2 * 1600 * 8),
+                "d2h_bytes_per_step": int(767040 * 4 + 1601 * 4), "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
+                "api": "infer.modules.vc.VC.vc_single (host numpy in, host int16 out)"},
+        "gpu_launches": int(launches * args.steps),
+        "gpu_launches_per_step": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "gemm_tc_kernel<*> (all implicit-GEMM launches of one utterance)",
+                     "launches_per_step": int(gn.value // 3), "ms_per_step": gemm_ms_per_step, "peak_source": pk_src,
+                     "algorithmic_flops_per_step": ALGO_FLOPS},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # bounded CPU sample: ONE full utterance through the oracle pipeline on the host cores
+        from oracle import ivf as OI, pipeline as OP, weights as OW
+        torch.set_num_threads(os.cpu_count())
+        class _L:  # reuse the already built layout for the oracle index (membership is data, not arithmetic)
+            pass
+        assign = np.empty(lay.vectors.shape[0], dtype=np.int64)
+        for l in range(len(lay.list_off) - 1):
+            assign[lay.list_ids[lay.list_off[l]:lay.list_off[l + 1]]] = l
+        oidx = OI.IVFFlat(lay.centroids, lay.vectors, assign)
+        pipe = OP.OraclePipeline(48000, 3, 10, 60, 65, OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234), OW.V2_48K_CONFIG)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            pipe.pipeline(0, audio.copy(), 0, "rmvpe", oidx, 0.75, 1, 48000, 0, 0.25, "v2", 0.33)
+            dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": OUT_SAMPLES / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "1 full 10 s utterance (oracle pipeline, torch CPU fp32, all cores), no warm-up"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

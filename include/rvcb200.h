@@ -32,6 +32,10 @@ const char* rvcb_last_error(void);
 unsigned long long rvcb_launch_count(void); /* kernels launched by this library so far */
 const char* rvcb_version(void);
 
+/* per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline); begin resets, end syncs and sums */
+int rvcb_prof_begin(void);
+int rvcb_prof_end(double* gemm_ms, unsigned long long* gemm_launches);
+
 /* ---- weight container (host fp32 tensors keyed by the reference's state_dict names) ------
  * replaces: torch.load + load_state_dict in rvc/synthesizer.py:10-35, rvc/f0/models.py:9-11,
  * infer/modules/vc/utils.py:24-36 (the Python side reads the .pth/.pt and hands tensors over). */

@@ -85,3 +85,14 @@ extern "C" int rvcb_upsample_protect(const float* d_feats, const float* d_feats0
     rvcb::upsample_protect(d_feats, d_feats0, T_h, C, d_pitchf, T, protect, d_out, (cudaStream_t)stream);
     RVCB_API_END
 }
+
+extern "C" int rvcb_prof_begin(void) {
+    RVCB_API_BEGIN
+    rvcb::gemm_prof_begin();
+    RVCB_API_END
+}
+extern "C" int rvcb_prof_end(double* gemm_ms, unsigned long long* gemm_launches) {
+    RVCB_API_BEGIN
+    rvcb::gemm_prof_end(gemm_ms, gemm_launches);
+    RVCB_API_END
+}

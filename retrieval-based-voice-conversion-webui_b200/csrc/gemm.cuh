@@ -73,6 +73,9 @@ void gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // Dispatch used by the model graphs.
 void gemm(const GemmArgs& g, cudaStream_t stream);
 
+void gemm_prof_begin();
+void gemm_prof_end(double* ms_total, unsigned long long* launches);
+
 // helpers to fill segments
 inline void seg_linear(GemmArgs& g, int K) {
     g.nseg = 1;

@@ -12,6 +12,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <vector>
 
 namespace rvcb {
 
@@ -451,6 +452,39 @@ static void encode_map(CUtensorMap* map, const void* base, int rank, const cuuin
     RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+void gemm_prof_begin() {
+    for (auto& e : g_prof_events) g_prof_pool.push_back(e);
+    g_prof_events.clear();
+    g_prof_on = true;
+}
+void gemm_prof_end(double* ms_total, unsigned long long* launches) {
+    g_prof_on = false;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    double tot = 0;
+    for (auto& e : g_prof_events) {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
+        tot += ms;
+    }
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = g_prof_events.size();
+}
+static std::pair<cudaEvent_t, cudaEvent_t> prof_get() {
+    if (!g_prof_pool.empty()) {
+        auto e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    return {a, b};
+}
+
 template <int BN, int BK>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& p, cudaStream_t stream) {
     using C = Cfg<BN, BK>;
@@ -464,8 +498,17 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
         configured = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{};
+    if (g_prof_on) {
+        ev = prof_get();
+        CUDA_CHECK(cudaEventRecord(ev.first, stream));
+    }
     gemm_tc_kernel<BN, BK><<<grid, kThreads, C::SMEM, stream>>>(ta, tb, p);
     KERNEL_CHECK();
+    if (g_prof_on) {
+        CUDA_CHECK(cudaEventRecord(ev.second, stream));
+        g_prof_events.push_back(ev);
+    }
     count_launch();
 }
 

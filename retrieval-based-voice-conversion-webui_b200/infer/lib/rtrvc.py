@@ -1,0 +1,122 @@
+"""Drop-in for ``infer.lib.rtrvc.RVC`` (infer/lib/rtrvc.py:19-274): the realtime engine gui.py drives
+(one rolling window per block).  Same constructor arguments, attributes (tgt_sr, if_f0, version), setters
+and ``infer(input_wav, block_frame_16k, skip_head, return_length, f0method, protect)``."""
+from __future__ import annotations
+
+import os
+from pathlib import Path
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from rvc.f0 import Generator
+from rvc.synthesizer import get_synthesizer, load_synthesizer
+from rvc_b200 import engine, faiss_io
+from infer.modules.vc.utils import load_hubert
+
+
+class RVC:
+    def __init__(self, key, formant, pth_path, index_path, index_rate, n_cpu: int = os.cpu_count(), device: str = "cuda:0",
+                 use_jit: bool = False, is_half: bool = False, is_dml: bool = False, hubert_model=None, rmvpe_state_dict=None):
+        self.device = torch.device(device if "cuda" in str(device) else "cuda:0")
+        self.f0_up_key = key
+        self.formant_shift = formant
+        self.sr = 16000
+        self.window = 160
+        self.n_cpu = n_cpu
+        self.is_half = is_half
+        self.index_path = index_path
+        self.index_rate = index_rate
+        if index_rate > 0:
+            self._load_index()
+        self.pth_path = pth_path
+        self.cache_pitch = torch.zeros(1024, device=self.device, dtype=torch.long)
+        self.cache_pitchf = torch.zeros(1024, device=self.device, dtype=torch.float32)
+        self.resample_kernel = {}
+        self.f0_gen = Generator(rmvpe_state_dict or Path(os.environ.get("rmvpe_root", "assets/rmvpe")), is_half, 0, self.device,
+                                self.window, self.sr)
+        self.hubert = hubert_model if hubert_model is not None else load_hubert(self.device, is_half)
+        if isinstance(pth_path, dict):
+            self.net_g, cpt = get_synthesizer(pth_path, self.device)
+        else:
+            self.net_g, cpt = load_synthesizer(pth_path, self.device)
+        self.tgt_sr = cpt["config"][-1]
+        self.if_f0 = cpt.get("f0", 1)
+        self.version = cpt.get("version", "v1")
+
+    def _load_index(self):
+        if isinstance(self.index_path, engine.Index):
+            self.index = self.index_path
+        else:
+            self.index = engine.Index.from_oracle_layout(faiss_io.read_index(self.index_path), self.device.index or 0)
+        self.big_npy = self.index.vectors
+
+    def set_key(self, new_key): self.f0_up_key = new_key
+    def set_formant(self, new_formant): self.formant_shift = new_formant
+
+    def set_index_rate(self, new_index_rate):
+        if new_index_rate > 0 and self.index_rate <= 0:
+            self._load_index()
+        self.index_rate = new_index_rate
+
+    @torch.no_grad()
+    def infer(self, input_wav: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method: Union[tuple, str],
+              protect: float = 1.0) -> torch.Tensor:
+        feats = input_wav.float().to(self.device)
+        if feats.dim() == 2:
+            feats = feats.mean(-1)
+        feats = feats.view(1, -1)
+        logits = self.hubert.extract_features(source=feats, padding_mask=None, output_layer=9 if self.version == "v1" else 12)
+        feats = self.hubert.final_proj(logits[0]) if self.version == "v1" else logits[0]
+        feats = torch.cat((feats, feats[:, -1:, :]), 1)[0]                       # rtrvc.py:163
+        feats0 = feats.clone() if (protect < 0.5 and self.if_f0 == 1) else None
+        try:
+            if hasattr(self, "index") and self.index_rate > 0:
+                tail = feats[skip_head // 2:]
+                D, I = self.index.search_device(tail, 8)
+                if bool((I >= 0).all()):                                        # rtrvc.py:173
+                    feats[skip_head // 2:] = self.index.blend_device(tail, D, I, self.index_rate)
+        except Exception:
+            pass
+        p_len = input_wav.shape[0] // self.window
+        factor = pow(2, self.formant_shift / 12)
+        return_length2 = int(np.ceil(return_length * factor))
+        cache_pitch = cache_pitchf = None
+        pitch = pitchf = None
+        if isinstance(f0method, tuple):
+            pitch, pitchf = f0method
+            pitch = torch.tensor(pitch, device=self.device).unsqueeze(0).long()
+            pitchf = torch.tensor(pitchf, device=self.device).unsqueeze(0).float()
+            cache_pitch, cache_pitchf = pitch[:, -p_len:], pitchf[:, -p_len:] * return_length2 / return_length
+        elif self.if_f0 == 1:
+            f0_extractor_frame = block_frame_16k + 800
+            if f0method == "rmvpe":
+                f0_extractor_frame = 5120 * ((f0_extractor_frame - 1) // 5120 + 1) - self.window
+            c, f = self.f0_gen.calculate(input_wav[-f0_extractor_frame:], None, self.f0_up_key - self.formant_shift, f0method, None)
+            pitch = torch.from_numpy(c).long().to(self.device)
+            pitchf = torch.from_numpy(np.asarray(f)).float().to(self.device)
+            shift = block_frame_16k // self.window
+            self.cache_pitch[:-shift] = self.cache_pitch[shift:].clone()
+            self.cache_pitchf[:-shift] = self.cache_pitchf[shift:].clone()
+            self.cache_pitch[4 - pitch.shape[0]:] = pitch[3:-1]
+            self.cache_pitchf[4 - pitch.shape[0]:] = pitchf[3:-1]
+            cache_pitch = self.cache_pitch[None, -p_len:]
+            cache_pitchf = self.cache_pitchf[None, -p_len:] * return_length2 / return_length
+        use_protect = protect < 0.5 and pitch is not None and pitchf is not None and feats0 is not None
+        pf = None
+        if use_protect:
+            pf = torch.ones(p_len, device=self.device)
+            n = min(p_len, pitchf.reshape(-1).shape[0])
+            pf[:n] = pitchf.reshape(-1)[:n]
+        phone = engine.upsample_protect(feats, feats0 if use_protect else None, pf, p_len, protect if use_protect else 1.0)
+        out = self.net_g.infer(phone.unsqueeze(0), torch.tensor([p_len], device=self.device), torch.tensor([0], device=self.device),
+                               pitch=cache_pitch, pitchf=cache_pitchf, skip_head=skip_head, return_length=return_length,
+                               return_length2=return_length2).squeeze(1).float()
+        upp_res = int(np.floor(factor * self.tgt_sr // 100))
+        if upp_res != self.tgt_sr // 100:
+            from torchaudio.transforms import Resample
+            if upp_res not in self.resample_kernel:
+                self.resample_kernel[upp_res] = Resample(orig_freq=upp_res, new_freq=self.tgt_sr // 100, dtype=torch.float32).to(self.device)
+            out = self.resample_kernel[upp_res](out[:, : return_length * upp_res])
+        return out.squeeze()

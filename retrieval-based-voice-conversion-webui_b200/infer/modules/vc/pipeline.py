@@ -1,0 +1,205 @@
+"""Drop-in for ``infer.modules.vc.pipeline.Pipeline`` (infer/modules/vc/pipeline.py:48-366).
+
+Same constructor, ``vc`` and ``pipeline`` signatures, ``times`` accounting and return conventions; the
+stages between the host DSP run on the B200 without the reference's four host round-trips per chunk
+(pipeline.py:118, 135-138, 172-174; rmvpe.py:109): HuBERT features, IVF-Flat search + blend, x2 upsample
++ protect mix, f0 and the synthesizer all stay on the device; one D2H copy returns the chunk's waveform.
+"""
+from __future__ import annotations
+
+import os
+import traceback
+import logging
+from pathlib import Path
+from time import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy import signal
+
+from rvc.f0 import Generator
+from rvc_b200 import engine, faiss_io
+
+logger = logging.getLogger(__name__)
+
+bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)     # pipeline.py:23
+
+
+def _rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
+    """librosa.feature.rms (center=True, zero padding) -> [1, n_frames]"""
+    pad = frame_length // 2
+    yp = np.pad(y.astype(np.float32), (pad, pad), mode="constant")
+    n = 1 + (len(yp) - frame_length) // hop_length
+    idx = np.arange(frame_length)[None, :] + hop_length * np.arange(n)[:, None]
+    return np.sqrt(np.mean(np.abs(yp[idx]) ** 2, axis=1, keepdims=True)).T.astype(np.float32)
+
+
+def change_rms(data1, sr1, data2, sr2, rate):     # pipeline.py:26-45
+    rms1 = torch.from_numpy(_rms(data1, sr1 // 2 * 2, sr1 // 2))
+    rms2 = torch.from_numpy(_rms(data2, sr2 // 2 * 2, sr2 // 2))
+    rms1 = F.interpolate(rms1.unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
+    rms2 = F.interpolate(rms2.unsqueeze(0), size=data2.shape[0], mode="linear").squeeze()
+    rms2 = torch.max(rms2, torch.zeros_like(rms2) + 1e-6)
+    data2 *= (torch.pow(rms1, torch.tensor(1 - rate)) * torch.pow(rms2, torch.tensor(rate - 1))).numpy()
+    return data2
+
+
+class Pipeline(object):
+    def __init__(self, tgt_sr, config):
+        self.x_pad, self.x_query, self.x_center, self.x_max, self.is_half = (
+            config.x_pad, config.x_query, config.x_center, config.x_max, config.is_half)
+        self.sr = 16000
+        self.window = 160
+        self.t_pad = self.sr * self.x_pad
+        self.t_pad_tgt = tgt_sr * self.x_pad
+        self.t_pad2 = self.t_pad * 2
+        self.t_query = self.sr * self.x_query
+        self.t_center = self.sr * self.x_center
+        self.t_max = self.sr * self.x_max
+        self.device = torch.device(config.device if "cuda" in str(config.device) else "cuda:0")
+        rmvpe_root = getattr(config, "rmvpe_state_dict", None) or Path(os.environ.get("rmvpe_root", "assets/rmvpe"))
+        self.f0_gen = Generator(rmvpe_root, self.is_half, self.x_pad, self.device, self.window, self.sr)
+        self._index_cache = {}
+
+    # -----------------------------------------------------------------------------------------
+    def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+        feats = torch.from_numpy(np.ascontiguousarray(audio0, dtype=np.float32))
+        if feats.dim() == 2:
+            feats = feats.mean(-1)
+        assert feats.dim() == 1, feats.dim()
+        feats = feats.view(1, -1)
+        padding_mask = None          # all-False in the reference (pipeline.py:100)
+        t0 = time()
+        with torch.no_grad():
+            logits = model.extract_features(source=feats.to(self.device, non_blocking=True), padding_mask=padding_mask,
+                                            output_layer=9 if version == "v1" else 12)
+            feats = model.final_proj(logits[0]) if version == "v1" else logits[0]
+        use_protect = protect < 0.5 and pitch is not None and pitchf is not None
+        feats0 = feats[0] if use_protect else None
+        f = feats[0]
+        if index is not None and big_npy is not None and index_rate != 0:
+            if isinstance(index, engine.Index):
+                D, I = index.search_device(f, 8)                       # IVF-Flat nprobe=1, k=8 on the device
+                f = index.blend_device(f, D, I, index_rate)
+            else:   # foreign index object (e.g. real faiss): the reference's host path, pipeline.py:118-138
+                npy = f.cpu().numpy().astype("float32")
+                try:
+                    score, ix = index.search(npy, k=8)
+                except Exception:
+                    raise Exception("index mistatch")
+                weight = np.square(1 / score)
+                weight /= weight.sum(axis=1, keepdims=True)
+                npy = np.sum(big_npy[ix] * np.expand_dims(weight, axis=2), axis=1)
+                f = torch.from_numpy(npy.astype(np.float32)).to(self.device) * index_rate + (1 - index_rate) * f
+        t1 = time()
+        p_len = audio0.shape[0] // self.window
+        if 2 * f.shape[0] < p_len:
+            p_len = 2 * f.shape[0]
+            if pitch is not None and pitchf is not None:
+                pitch = pitch[:, :p_len]
+                pitchf = pitchf[:, :p_len]
+        # x2 nearest upsample + protect mix (pipeline.py:140-160) in one kernel; all 2*T_h frames go to net_g
+        T2 = 2 * f.shape[0]
+        pf_full = None
+        if use_protect:
+            pf_full = torch.ones(T2, device=self.device)
+            pf_full[:pitchf.shape[1]] = pitchf[0, :T2]
+        phone = engine.upsample_protect(f, feats0, pf_full, T2, protect if use_protect else 1.0)
+        with torch.no_grad():
+            T = phone.shape[0]
+            if pitch is not None and pitch.shape[1] < T:      # masks use p_len; frames past it are ignored downstream
+                phone = phone[: pitch.shape[1]]
+                T = phone.shape[0]
+            audio1 = net_g.infer(phone.unsqueeze(0), torch.tensor([T], device=self.device), sid,
+                                 pitch=None if pitch is None else pitch[:, :T], pitchf=None if pitchf is None else pitchf[:, :T])[0, 0]
+            audio1 = audio1.data.cpu().float().numpy()
+        t2 = time()
+        times[0] += t1 - t0
+        times[2] += t2 - t1
+        return audio1
+
+    # -----------------------------------------------------------------------------------------
+    def _load_index(self, file_index):
+        """Replaces faiss.read_index + reconstruct_n on EVERY call (pipeline.py:213-215) with a cached
+        device-resident index."""
+        if isinstance(file_index, engine.Index):
+            return file_index, file_index.vectors
+        key = (file_index, os.path.getmtime(file_index))
+        if key not in self._index_cache:
+            layout = faiss_io.read_index(file_index)
+            self._index_cache = {key: engine.Index.from_oracle_layout(layout, self.device.index or 0)}
+        ix = self._index_cache[key]
+        return ix, ix.vectors
+
+    def pipeline(self, model, net_g, sid, audio, times, f0_up_key, f0_method, file_index, index_rate, if_f0, filter_radius, tgt_sr,
+                 resample_sr, rms_mix_rate, version, protect, f0_file=None):
+        index = big_npy = None
+        if index_rate != 0 and (isinstance(file_index, engine.Index) or (file_index != "" and os.path.exists(file_index))):
+            try:
+                index, big_npy = self._load_index(file_index)
+            except Exception:
+                traceback.print_exc()
+                index = big_npy = None
+        audio = signal.filtfilt(bh, ah, audio)
+        audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
+        opt_ts = []
+        if audio_pad.shape[0] > self.t_max:
+            # pipeline.py:224-227 sums 160 shifted copies; a cumulative sum gives the same window sums
+            cs = np.concatenate([[0.0], np.cumsum(np.abs(audio_pad))])
+            audio_sum = cs[self.window: self.window + audio.shape[0]] - cs[: audio.shape[0]]
+            for t in range(self.t_center, audio.shape[0], self.t_center):
+                seg = audio_sum[t - self.t_query: t + self.t_query]
+                opt_ts.append(t - self.t_query + int(np.argmin(seg)))
+        s = 0
+        audio_opt = []
+        t = None
+        t1 = time()
+        audio_pad = np.pad(audio, (self.t_pad, self.t_pad), mode="reflect")
+        p_len = audio_pad.shape[0] // self.window
+        inp_f0 = None
+        if hasattr(f0_file, "name"):
+            try:
+                with open(f0_file.name, "r") as f:
+                    raw_lines = f.read()
+                    if len(raw_lines) > 0:
+                        inp_f0 = np.array([[float(i) for i in line.split(",")] for line in raw_lines.strip("\n").split("\n")], dtype="float32")
+            except Exception:
+                traceback.print_exc()
+        sid = torch.tensor(sid, device=self.device).unsqueeze(0).long()
+        pitch, pitchf = None, None
+        if if_f0:
+            if if_f0 == 1:
+                pitch, pitchf = self.f0_gen.calculate(audio_pad, p_len, f0_up_key, f0_method, filter_radius, inp_f0)
+            elif if_f0 == 2:
+                pitch, pitchf = f0_method
+            pitch = pitch[:p_len]
+            pitchf = pitchf[:p_len].astype(np.float32)
+            pitch = torch.tensor(pitch, device=self.device).unsqueeze(0).long()
+            pitchf = torch.tensor(pitchf, device=self.device).unsqueeze(0).float()
+        t2 = time()
+        times[1] += t2 - t1
+        W = self.window
+        for t in opt_ts:
+            t = t // W * W
+            audio_opt.append(self.vc(model, net_g, sid, audio_pad[s: t + self.t_pad2 + W],
+                                     pitch[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
+                                     pitchf[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
+                                     times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
+            s = t
+        audio_opt.append(self.vc(model, net_g, sid, audio_pad[t:],
+                                 (pitch[:, t // W:] if t is not None else pitch) if if_f0 else None,
+                                 (pitchf[:, t // W:] if t is not None else pitchf) if if_f0 else None,
+                                 times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
+        audio_opt = np.concatenate(audio_opt)
+        if rms_mix_rate != 1:
+            audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
+        if tgt_sr != resample_sr >= 16000:
+            import torchaudio          # librosa.resample (pipeline.py:351-354) is not installed; host DSP stays on the CPU
+            audio_opt = torchaudio.functional.resample(torch.from_numpy(audio_opt.astype(np.float32)), tgt_sr, resample_sr).numpy()
+        audio_max = np.abs(audio_opt).max() / 0.99
+        max_int16 = 32768
+        if audio_max > 1:
+            max_int16 /= audio_max
+        audio_opt = audio_opt * max_int16
+        return audio_opt

@@ -1,0 +1,69 @@
+"""Drop-in for infer/modules/vc/utils.py:24-36 (load_hubert, index discovery)."""
+import os
+import pathlib
+
+import torch
+
+from rvc_b200.engine import Hubert
+
+
+def get_index_path_from_model(sid):
+    return next((f for f in [str(pathlib.Path(root, name))
+                             for path in [os.getenv("outside_index_root"), os.getenv("index_root")] if path
+                             for root, _, files in os.walk(path, topdown=False) for name in files
+                             if name.endswith(".index") and "trained" not in name] if sid.split(".")[0] in f), "")
+
+
+class _Permissive:
+    """Stand-in for classes pickled inside a fairseq checkpoint (fairseq is not a dependency here)."""
+    def __init__(self, *a, **k): pass
+    def __setstate__(self, s): self.__dict__.update(s if isinstance(s, dict) else {})
+
+
+def _load_fairseq_state_dict(path: str) -> dict:
+    import pickle
+
+    class U(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except Exception:
+                return type(name, (_Permissive,), {})
+
+    class PM:
+        Unpickler = U
+        load = staticmethod(lambda f, **k: U(f, **k).load())
+        __name__ = "pickle"
+    ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=PM)
+    return ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
+
+
+class HubertB200:
+    """Duck-type of the fairseq HubertModel object for the calls at pipeline.py:102-110 / rtrvc.py:154-162."""
+
+    def __init__(self, state_dict: dict, device="cuda:0"):
+        self.device = torch.device(device if "cuda" in str(device) else "cuda:0")
+        self._m = Hubert({k: v.float() for k, v in state_dict.items() if torch.is_tensor(v) and v.is_floating_point()},
+                         self.device.index or 0)
+
+    def half(self): return self
+    def float(self): return self
+    def eval(self): return self
+    def to(self, *a, **k): return self
+
+    @torch.no_grad()
+    def extract_features(self, source, padding_mask=None, mask=False, output_layer=None):
+        if source.dim() != 2 or source.shape[0] != 1:
+            raise ValueError("B=1 only (the reference callers never batch)")
+        if padding_mask is not None and bool(padding_mask.any()):
+            raise NotImplementedError("padding_mask with True entries (batched front door) is a 'next' row (SURVEY §8f-3)")
+        feats = self._m.extract(source[0].to(self.device), 12 if output_layer is None else int(output_layer))
+        return feats.unsqueeze(0), None
+
+    @torch.no_grad()
+    def final_proj(self, x):
+        return self._m.final_proj(x.reshape(-1, 768)).view(*x.shape[:-1], 256)
+
+
+def load_hubert(device, is_half, path: str = "assets/hubert/hubert_base.pt"):
+    return HubertB200(_load_fairseq_state_dict(path), device)

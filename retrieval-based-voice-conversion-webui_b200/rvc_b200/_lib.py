@@ -55,6 +55,8 @@ SIGNATURES = {
     "rvcb_last_error": (C.c_char_p, []),
     "rvcb_launch_count": (C.c_ulonglong, []),
     "rvcb_version": (C.c_char_p, []),
+    "rvcb_prof_begin": (_I, []),
+    "rvcb_prof_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "rvcb_weights_create": (_I, [C.POINTER(_P)]),
     "rvcb_weights_add": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
     "rvcb_weights_destroy": (None, [_P]),

@@ -1,0 +1,88 @@
+"""GPU end-to-end: the drop-in Pipeline / VC / rtrvc.RVC front doors against the oracle pipeline on one utterance."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg:
+    x_pad, x_query, x_center, x_max, is_half = 1, 6, 38, 41, False
+    device = "cuda:0"
+    rmvpe_state_dict = None
+
+
+def _setup(seconds=2.0, n_index=3000):
+    from oracle import ivf as OI, pipeline as OP, weights as OW
+    hw, rw, sw = OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234)
+    audio = OW.synth_voice(seconds, seed=4).numpy()
+    idx = OI.build_ivf(OW.index_vectors(n_index, 768, 1).numpy(), None, seed=0, exact_assign=True)
+    return OI, OP, OW, hw, rw, sw, audio, idx
+
+
+def test_pipeline_matches_oracle_with_shared_pitch_and_noise():
+    from infer.modules.vc.pipeline import Pipeline
+    from infer.modules.vc.utils import HubertB200
+    from rvc.synthesizer import get_synthesizer
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup()
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    op = OP.OraclePipeline(48000, 1, 6, 38, 41, hw, rw, sw, OW.V2_48K_CONFIG, noise_seed=3)
+    with torch.no_grad():
+        ref = op.pipeline(0, audio.copy(), 0, "rmvpe", idx, 0.75, 1, 48000, 0, 0.25, "v2", 0.33)
+    pitch, pitchf = op.pitch[0].numpy(), op.pitchf[0].numpy()
+    pipe = Pipeline(48000, cfg)
+    hub = HubertB200(hw, "cuda:0")
+    net_g, cpt = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
+    gidx = Index.from_oracle_layout(idx)
+    # 1) same f0 track + same noise -> isolates HuBERT + retrieval + synthesizer
+    net_g.set_noise(*op.taps[0]["noise"])
+    times = [0, 0, 0]
+    out = pipe.pipeline(hub, net_g, 0, audio.copy(), times, 0, (pitch, pitchf.astype(np.float64)), gidx, 0.75, 2, 3, 48000, 0, 0.25, "v2", 0.33)
+    assert out.shape == ref.shape
+    # retrieval indices: HuBERT feature error (~1e-2) can flip near-ties; require >= 97 % identical neighbours
+    feats = hub.extract_features(source=torch.from_numpy(np.pad(__import__("scipy.signal").signal.filtfilt(
+        __import__("infer.modules.vc.pipeline", fromlist=["bh"]).bh, __import__("infer.modules.vc.pipeline", fromlist=["ah"]).ah, audio),
+        (16000, 16000), mode="reflect").astype(np.float32))[None].cuda(), output_layer=12)[0][0]
+    _, I = gidx.search_device(feats, 8)
+    same = (I.cpu().numpy() == op.taps[0]["ix"]).mean()
+    assert same >= 0.97, same
+    err = np.abs(out - ref).max() / 32768.0
+    assert err < 2e-2, f"end-to-end max abs err (full scale) {err}"
+    # 2) the full path with its own RMVPE f0: coarse pitch agrees on >= 95 % of frames, f0 within 1 % where both voiced
+    c2, f2 = pipe.f0_gen.calculate(np.pad(__import__("scipy.signal").signal.filtfilt(
+        __import__("infer.modules.vc.pipeline", fromlist=["bh"]).bh, __import__("infer.modules.vc.pipeline", fromlist=["ah"]).ah, audio),
+        (16000, 16000), mode="reflect").astype(np.float32), len(pitch), 0, "rmvpe", 3)
+    assert (c2[: len(pitch)] == pitch).mean() >= 0.95
+    both = (f2[: len(pitchf)] > 0) & (pitchf > 0)
+    assert np.median(np.abs(f2[: len(pitchf)][both] / pitchf[both] - 1)) < 1e-2
+
+
+def test_vc_facade_and_realtime_engine_run():
+    from infer.lib.rtrvc import RVC
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.5, 1200)
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    upd = vc.get_vc(OW.synth_cpt(1234, "v2"))
+    assert upd["maximum"] == 109
+    gidx = Index.from_oracle_layout(idx)
+    info, (sr, wav) = vc.vc_single(0, audio, 0, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+    assert info.startswith("Success") and sr == 48000 and wav.dtype == np.int16 and wav.shape[0] == 48000 * 3 // 2
+    assert np.isfinite(wav.astype(np.float32)).all() and np.abs(wav).max() > 100
+    # error convention: exceptions become the info string (modules.py:196-199)
+    info, out = vc.vc_single(0, audio, 0, None, "harvest", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+    assert out is None and "harvest" in info
+    # realtime block (gui.py sizes): 43520-sample window, skip_head 250, return_length 21
+    rt = RVC(0, 0, OW.synth_cpt(1234, "v2"), gidx, 0.5, device="cuda:0", hubert_model=vc.hubert_model, rmvpe_state_dict=rw)
+    assert rt.tgt_sr == 48000 and rt.if_f0 == 1 and rt.version == "v2"
+    win = torch.from_numpy(OW.synth_voice(2.72, seed=9).numpy()[:43520]).cuda()
+    y = rt.infer(win, 2560, 250, 21, "rmvpe")
+    assert y.shape == (21 * 480,) and torch.isfinite(y).all()
+    y2 = rt.infer(win, 2560, 250, 21, "rmvpe", protect=0.33)
+    assert y2.shape == (10080,)
