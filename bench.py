@@ -145,19 +145,9 @@ def main():
     # index: rank 0 builds the layout; the optional one-time broadcast over NCCL shares it (the only collective of the path)
     if rank == 0:
         lay = build_ivf_layout(SY.index_vectors(100000, 768, 0).numpy(), None, seed=0, device=str(dev))
-        blob = [lay.centroids, lay.vectors, lay.list_off, lay.list_ids]
     if world > 1:
-        shapes = [None]
-        if rank == 0:
-            shapes = [[(b.shape, str(b.dtype)) for b in blob]]
-        dist.broadcast_object_list(shapes, src=0)
-        tens = []
-        for i, (shp, dt) in enumerate(shapes[0]):
-            t = torch.from_numpy(blob[i]).to(dev) if rank == 0 else torch.empty(shp, dtype=getattr(torch, dt.replace("float32", "float32")), device=dev)
-            dist.broadcast(t, src=0)
-            tens.append(t.cpu().numpy())
-        from rvc_b200.faiss_io import IVFLayout
-        lay = IVFLayout(*tens)
+        from rvc_b200.dist_utils import broadcast_layout
+        lay = broadcast_layout(lay if rank == 0 else None, 0, str(dev))
     index = Index.from_oracle_layout(lay, local_rank)
 
     audio = SY.synth_voice(UTT_SECONDS, seed=rank).numpy()          # each rank converts its own utterances (weak scaling)

@@ -1,0 +1,110 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own modules (imported from /root/reference in the build
+container) and, for HuBERT (un-vendored fairseq), transformers.HubertModel.  Weights/inputs come from seeds, so only the
+small outputs are stored.  Run:  python tests/golden/make_golden.py"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_grad_enabled(False)
+
+# import the REFERENCE's packages first: the product package mirrors the same module names (rvc.*, infer.*)
+from rvc.synthesizer import get_synthesizer  # noqa: E402
+from rvc.f0.e2e import E2E  # noqa: E402
+from rvc.f0.f0 import F0Predictor  # noqa: E402
+assert "/root/reference" in get_synthesizer.__code__.co_filename
+
+from oracle import weights as OW  # noqa: E402  (seeded generators only)
+
+
+def synth():
+    cpt = OW.synth_cpt(1234, "v2")
+    net_g, _ = get_synthesizer(cpt, "cpu")
+    T = 24
+    g = torch.Generator().manual_seed(11)
+    phone = (torch.randn(1, T, 768, generator=g) * 0.5).half().float()     # stored as fp16, exactly representable
+    pitchf = torch.full((1, T), 0.0)
+    pitchf[:, 3:20] = 200 + 30 * torch.sin(torch.arange(17) / 3.0)
+    mn, mx = 1127 * math.log(1 + 50 / 700), 1127 * math.log(1 + 1100 / 700)
+    fm = 1127 * torch.log(1 + pitchf / 700)
+    pitch = torch.round(torch.where(fm > 0, (fm - mn) * 254 / (mx - mn) + 1, fm).clamp(1, 255)).long()
+    torch.manual_seed(2024)
+    out = net_g.infer(phone, torch.tensor([T]), torch.tensor([5]), pitch, pitchf)
+    torch.manual_seed(2025)
+    out_rt = net_g.infer(phone, torch.tensor([T]), torch.tensor([5]), pitch, pitchf, skip_head=16, return_length=6, return_length2=6)
+    np.savez_compressed(os.path.join(OUT, "synth_v2_48k_T24.npz"), phone=phone.numpy().astype(np.float16), pitch=pitch.numpy(),
+                        pitchf=pitchf.numpy(), out=out[0, 0].numpy(), out_rt=out_rt[0, 0].numpy(), seed=2024, seed_rt=2025, sid=5)
+
+
+def rmvpe():
+    m = E2E(4, 1, (2, 2)).eval()
+    m.load_state_dict(OW.rmvpe_weights(4321))
+    g = torch.Generator().manual_seed(5)
+    mel = torch.randn(1, 128, 64, generator=g) * 3 - 4.5
+    hid = m(mel)[0].numpy()
+    # decode with the reference's literal per-frame loop (rmvpe.py:119-137)
+    cents_mapping = np.pad(20 * np.arange(360) + 1997.3794084376191, (4, 4))
+    sal = hid.copy()
+    center = np.argmax(sal, axis=1); salp = np.pad(sal, ((0, 0), (4, 4))); center += 4
+    ts, tc = [], []
+    for i in range(salp.shape[0]):
+        ts.append(salp[:, center[i] - 4:center[i] + 5][i]); tc.append(cents_mapping[center[i] - 4:center[i] + 5])
+    ts, tc = np.array(ts), np.array(tc)
+    dev = np.sum(ts * tc, 1) / np.sum(ts, 1); dev[np.max(salp, axis=1) <= 0.03] = 0
+    f0 = 10 * (2 ** (dev / 1200)); f0[f0 == 10] = 0
+    fp = F0Predictor()
+    rng = np.random.RandomState(3)
+    tracks, outs = [], []
+    for _ in range(6):
+        x = np.abs(rng.randn(50)) * 120 * (rng.rand(50) > 0.45)
+        tracks.append(x)
+        outs.append(fp._interpolate_f0(fp._resize_f0(x.copy(), 37))[0])
+    np.savez_compressed(os.path.join(OUT, "rmvpe_e2e_64.npz"), mel=mel.numpy().astype(np.float32), hidden=hid, f0=f0,
+                        tracks=np.array(tracks), resized=np.array(outs))
+
+
+def f0_fixtures():
+    z = np.load("/root/reference/infer/modules/vc/lgdsng.npz")
+    np.savez_compressed(os.path.join(OUT, "ref_fixtures_f0.npz"), lgdsng_pitch=z["pitch"], lgdsng_pitchf=z["pitchf"],
+                        mute_2a_f0=np.load("/root/reference/logs/mute/2a_f0/mute.wav.npy"),
+                        mute_2b_f0nsf=np.load("/root/reference/logs/mute/2b-f0nsf/mute.wav.npy"))
+
+
+def hubert():
+    import re
+    from transformers import HubertConfig, HubertModel
+    w = OW.hubert_weights(777)
+    m = HubertModel(HubertConfig()).eval()
+    sd = m.state_dict()
+    new = {}
+    for k, v in w.items():
+        if k.startswith("final_proj"):
+            continue
+        k = k.replace("feature_extractor.conv_layers.0.2.", "feature_extractor.conv_layers.0.layer_norm.")
+        k = re.sub(r"feature_extractor\.conv_layers\.(\d)\.0\.weight", r"feature_extractor.conv_layers.\1.conv.weight", k)
+        if k.startswith("layer_norm."):
+            k = "feature_projection." + k
+        k = k.replace("post_extract_proj.", "feature_projection.projection.")
+        k = k.replace("encoder.pos_conv.0.weight_g", "encoder.pos_conv_embed.conv.parametrizations.weight.original0")
+        k = k.replace("encoder.pos_conv.0.weight_v", "encoder.pos_conv_embed.conv.parametrizations.weight.original1")
+        k = k.replace("encoder.pos_conv.0.bias", "encoder.pos_conv_embed.conv.bias")
+        k = k.replace("self_attn.", "attention.").replace("self_attn_layer_norm", "layer_norm")
+        k = k.replace("fc1.", "feed_forward.intermediate_dense.").replace("fc2.", "feed_forward.output_dense.")
+        assert k in sd and sd[k].shape == v.shape, k
+        new[k] = v
+    m.load_state_dict(new, strict=False)
+    wav = OW.synth_voice(0.5, seed=6)[None]
+    hs = m(wav, output_hidden_states=True).hidden_states
+    np.savez_compressed(os.path.join(OUT, "hubert_hf_0p5s.npz"), layer9=hs[9][0].numpy(), layer12=hs[12][0].numpy())
+
+
+if __name__ == "__main__":
+    synth(); rmvpe(); f0_fixtures(); hubert()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,117 @@
+"""CPU: host-side logic, the C-ABI library surface, the numpy IVF oracle's own invariants, and the N>1 plumbing (gloo)."""
+import os
+import re
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from rvc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "rvcb200.h")).read()
+    declared = set(re.findall(r"\b(rvcb_[a-z0-9_]+)\s*\(", hdr))
+    l = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(l, name), f"librvcb200.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in l.rvcb_version()
+
+
+def test_product_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rvc_b200 import synthetic as SY
+    from rvc.synthesizer import get_synthesizer
+    with pytest.raises(RuntimeError):
+        get_synthesizer(SY.synth_cpt(1, "v2"), "cuda:0")      # no CPU / PyTorch fallback on the product path
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "retrieval-based-voice-conversion-webui_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
+def test_f0post_matches_oracle_loops():
+    from oracle import rmvpe as ORM
+    from rvc_b200 import f0post
+    rng = np.random.RandomState(0)
+    for _ in range(400):
+        n = rng.randint(1, 60)
+        x = np.abs(rng.randn(n)) * 100 * (rng.rand(n) > rng.rand())
+        assert np.array_equal(ORM.interpolate_f0(x.copy()), f0post.interpolate_f0(x.copy()))
+        tl = rng.randint(1, 80)
+        assert np.array_equal(ORM.resize_f0(x.copy(), tl), f0post.resize_f0(x.copy(), tl))
+        a, b = ORM.post_process(x.copy(), 3), f0post.post_process(x.copy(), 3)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_ivf_oracle_invariants_and_index_file_roundtrip():
+    from oracle import ivf as OI, weights as OW
+    from rvc_b200 import faiss_io
+    vec = OW.index_vectors(700, 768, 3).numpy()
+    idx = OI.build_ivf(vec, 14, seed=1, exact_assign=True)
+    D, I = idx.search(vec[:50], 8)
+    assert np.array_equal(I[:, 0], np.arange(50)) and (D[:, 0] == 0).all()        # a stored vector finds itself
+    assert (np.diff(D, axis=1) >= 0).all()                                          # ascending
+    bf_D, bf_I = OI.brute_force_top1(vec[100:120] + 0.01, vec)
+    assert np.array_equal(bf_I, np.arange(100, 120))
+    ref = ((vec[100:120] + np.float32(0.01) - vec[100:120]).astype(np.float64) ** 2).sum(1)
+    assert np.allclose(bf_D, ref, rtol=1e-5)
+    # empty / short lists pad with (FLT_MAX, -1) like faiss
+    tiny = OI.build_ivf(vec[:60], 30, seed=0, exact_assign=True)
+    D, I = tiny.search(vec[:10] + 0.5, 8)
+    assert (I == -1).any() and (D[I == -1] == OI.FLT_MAX).all()
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "added_IVF14_Flat_nprobe_1_x_v2.index")
+        faiss_io.write_index(p, idx)
+        lay = faiss_io.read_index(p)
+        for f in ("centroids", "vectors", "list_off", "list_ids"):
+            assert np.array_equal(getattr(lay, f), getattr(idx, f))
+        faiss_io.save_layout(os.path.join(td, "x.npz"), idx)
+        assert np.array_equal(faiss_io.read_index(os.path.join(td, "x.npz")).vectors, idx.vectors)
+    # blend: numpy semantics incl. -1 ids and exact hits
+    feats = np.random.RandomState(0).randn(10, 768).astype(np.float32)
+    out = OI.blend(feats, D, I, tiny.vectors, 0.75)
+    assert out.shape == feats.shape and np.isfinite(out).all()
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(ROOT, "retrieval-based-voice-conversion-webui_b200"))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from rvc_b200 import dist_utils, synthetic as SY
+    from rvc_b200.index_build import build_ivf_layout
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lay = build_ivf_layout(SY.index_vectors(400, 768, 0).numpy(), 8, device="cpu") if rank == 0 else None
+    got = dist_utils.broadcast_layout(lay, 0, "cpu")
+    mine = dist_utils.shard(list(range(11)), rank, world)
+    t = torch.tensor([float(len(mine))])
+    dist.all_reduce(t)
+    q.put((rank, float(got.vectors.sum()), int(got.list_off[-1]), mine, float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_and_index_broadcast_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in ps]
+    (r0, s0, n0, m0, t0), (r1, s1, n1, m1, t1) = res
+    assert s0 == s1 and n0 == n1 == 400                     # identical index on both ranks
+    assert sorted(m0 + m1) == list(range(11)) and not set(m0) & set(m1)   # every utterance exactly once
+    assert t0 == t1 == 11.0
