@@ -4,13 +4,15 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring, mbarrier tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
 //                               tcgen05.commit releases smem slots / publishes the accumulator)
-//   warps 2..5  epilogue       (tcgen05.ld TMEM -> registers -> fused bias/act/residual -> global)
+//   warps 2..9  epilogue       (tcgen05.ld TMEM -> registers -> warp-private smem transpose -> fused
+//                               bias/act/residual with COALESCED residual loads and output stores)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // Conv taps are K-segments whose A tile is the same matrix at a shifted TMA coordinate;
 // zero padding comes from TMA out-of-bounds fill, so no im2col buffer ever exists.
 #include "gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -145,7 +147,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // 2 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int BM = 128;
 
 template <int BN, int BK>
@@ -154,9 +157,13 @@ struct Cfg {
     static constexpr int B_STAGE_RAW = BN * BK * 2;
     static constexpr int B_STAGE = (B_STAGE_RAW + 1023) / 1024 * 1024;
     static constexpr int STAGE = A_STAGE + B_STAGE;
-    static constexpr int STAGES = (196608 / STAGE) > 8 ? 8 : (196608 / STAGE);
+    static constexpr int CW = BN >= 32 ? 32 : 16;                 // epilogue chunk width (columns)
+    static constexpr int EPI_STRIDE = CW + 4;                     // floats per staged row (16B aligned, conflict-free)
+    static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;
+    static constexpr int PIPE_BUDGET = 226 * 1024 - EPI_BYTES - 2048;
+    static constexpr int STAGES = (PIPE_BUDGET / STAGE) > 8 ? 8 : (PIPE_BUDGET / STAGE);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr uint32_t TX_BYTES = A_STAGE + B_STAGE_RAW;
 };
 
@@ -175,6 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* tfull_bar = bars + 2 * C::STAGES;     // [2]
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -188,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -262,9 +270,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else {
-        // ======================= epilogue =======================
-        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-        const int row_in_tile = quarter * 32 + lane;
+        // ======================= epilogue (8 warps) =======================
+        // TMEM lane quarter = warp % 4 (hardware rule); the two warps sharing a quarter split the column chunks.
+        constexpr int CW = C::CW, ST = C::EPI_STRIDE, NV = CW / 4;     // NV float4 per staged row
+        constexpr int RPI = 32 / NV;                                   // rows covered by one warp-wide float4 access
+        constexpr int NIT = 32 / RPI;                                  // iterations to cover 32 rows
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int cgroup = ew >> 2;                                    // 0 / 1
+        float* stg = epi_smem + ew * 32 * ST;
+        const int c4 = lane % NV, rsub = lane / NV;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -272,136 +287,187 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int rem = tile - z * tiles_per_z;
             const int mt = rem / p.num_n_tiles;
             const int nt = rem - mt * p.num_n_tiles;
-            const int m = mt * BM + row_in_tile;
-            const bool row_ok = m < p.M;
+            const int m_warp0 = mt * BM + quarter * 32;                // first row of this warp's 32-row slab
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
-
-            // output row base (elements) for this thread
-            long orow;        // row index into the output matrices
-            if (p.up2_C == 0) {
-                orow = m;
-            } else {
-                orow = 0;     // computed per column group below
-            }
-            const float* r1 = p.res1 ? p.res1 + z * p.c_z + (long)m * p.ldres1 : nullptr;
-            const float* r2 = p.res2 ? p.res2 + z * p.c_z + (long)m * p.ldres2 : nullptr;
-            const float bias_row = (p.bias && p.bias_per_row && row_ok) ? p.bias[m] : 0.f;
             const float* biasz = p.bias ? p.bias + z * p.bias_z : nullptr;
+            const float bias_row = (p.bias && p.bias_per_row && (m_warp0 + lane) < p.M) ? p.bias[m_warp0 + lane] : 0.f;
+            const long zoff = z * p.c_z;
 
 #pragma unroll 1
-            for (int c = 0; c < BN / 16; ++c) {
-                uint32_t raw[16];
-                tmem_ld16(taddr + c * 16, raw);
-                tmem_ld_wait();
-                const int n0 = nt * BN + c * 16;
-                if (row_ok && n0 < p.N) {
-                    float v[16];
-                    const bool full = (n0 + 16 <= p.N);
+            for (int c = cgroup; c < BN / CW; c += 2) {
+                const int n0 = nt * BN + c * CW;
+                if (n0 >= p.N) break;                                   // warp-uniform
+                // ---- TMEM -> registers (thread = row) ----
+                float v[CW];
+                {
+                    uint32_t raw[16];
+                    tmem_ld16(taddr + c * CW, raw);
+                    if constexpr (CW == 32) {
+                        uint32_t raw2[16];
+                        tmem_ld16(taddr + c * CW + 16, raw2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(raw2[i]);
+                    } else {
+                        tmem_ld_wait();
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-                    if (p.bias) {
-                        if (p.bias_per_row) {
+                }
+                if (p.bias) {
+                    if (p.bias_per_row) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += bias_row;
-                        } else if (full) {
+                        for (int i = 0; i < CW; ++i) v[i] += bias_row;
+                    } else if (n0 + CW <= p.N) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 b = *reinterpret_cast<const float4*>(biasz + n0 + i);
-                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n0 + i < p.N) v[i] += biasz[n0 + i];
-                        }
-                    }
-                    if (r1) {
-                        if (full && p.vec_ok) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 b = *reinterpret_cast<const float4*>(r1 + n0 + i);
-                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n0 + i < p.N) v[i] += r1[n0 + i];
-                        }
-                    }
-                    if (p.gate) {
-                        // (tanh, sigmoid) column pairs -> N/2 outputs
-                        const int o0 = n0 >> 1;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (n0 + 2 * i + 1 < p.N) {
-                                const float g = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
-                                if (p.out32) p.out32[z * p.c_z + (long)m * p.ld32 + o0 + i] = g;
-                                if (p.out16) p.out16[z * p.c_z + (long)m * p.ld16 + o0 + i] = __float2half_rn(g);
-                            }
+                        for (int i = 0; i < CW; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(biasz + n0 + i));
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                         }
                     } else {
-                        if (p.act1 != ACT_NONE) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act1, p.act1_p);
-                        }
-                        if (p.alpha != 1.f) {
+                        for (int i = 0; i < CW; ++i)
+                            if (n0 + i < p.N) v[i] += __ldg(biasz + n0 + i);
+                    }
+                }
+                // ---- transpose through warp-private smem: afterwards lane = (row rsub + RPI*it, float4 column c4) ----
+                __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-                        }
-                        if (r2) {
-                            if (full && p.vec_ok) {
+                for (int i = 0; i < CW; i += 4)
+                    *reinterpret_cast<float4*>(stg + lane * ST + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+                const int col = n0 + 4 * c4;
+                const bool col_full = (col + 3 < p.N);
+                const bool vec = col_full && p.vec_ok;
+                float4 t[NIT];
 #pragma unroll
-                                for (int i = 0; i < 16; i += 4) {
-                                    const float4 b = *reinterpret_cast<const float4*>(r2 + n0 + i);
-                                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                                }
+                for (int it = 0; it < NIT; ++it) t[it] = *reinterpret_cast<const float4*>(stg + (rsub + RPI * it) * ST + 4 * c4);
+                // residual 1 (before the activation), coalesced
+                if (p.res1) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int m = m_warp0 + rsub + RPI * it;
+                        if (m < p.M && col < p.N) {
+                            const float* r = p.res1 + zoff + (long)m * p.ldres1 + col;
+                            if (vec) {
+                                const float4 q = *reinterpret_cast<const float4*>(r);
+                                t[it].x += q.x; t[it].y += q.y; t[it].z += q.z; t[it].w += q.w;
                             } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (n0 + i < p.N) v[i] += r2[n0 + i];
+                                t[it].x += r[0];
+                                if (col + 1 < p.N) t[it].y += r[1];
+                                if (col + 2 < p.N) t[it].z += r[2];
+                                if (col + 3 < p.N) t[it].w += r[3];
                             }
                         }
-                        long ocol = n0;
-                        if (p.up2_C) {
-                            // n = (a*2+b)*C + co ; input pixel m = i*W + j -> output pixel (2i+a, 2j+b)
-                            const int W = p.conv2d_W, Cc = p.up2_C;
-                            const int ab = n0 / Cc, co = n0 - ab * Cc;
-                            const int ii = m / W, jj = m - ii * W;
-                            orow = (long)(2 * ii + (ab >> 1)) * (2 * W) + 2 * jj + (ab & 1);
-                            ocol = co;
-                        }
-                        if (p.out32) {
-                            float* o = p.out32 + z * p.c_z + orow * p.ld32 + ocol;
-                            if (full && p.vec_ok) {
+                    }
+                }
+                if (p.gate) {
+                    // (tanh, sigmoid) column pairs -> N/2 outputs
 #pragma unroll
-                                for (int i = 0; i < 16; i += 4)
-                                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int it = 0; it < NIT; ++it) {
+                        const int m = m_warp0 + rsub + RPI * it;
+                        if (m < p.M && col + 1 < p.N) {
+                            const float g0 = tanhf(t[it].x) * (1.f / (1.f + expf(-t[it].y)));
+                            const long o = zoff + (long)m * (p.out16 ? p.ld16 : p.ld32) + (col >> 1);
+                            const bool two = (col + 3 < p.N);
+                            const float g1 = two ? tanhf(t[it].z) * (1.f / (1.f + expf(-t[it].w))) : 0.f;
+                            if (p.out16) {
+                                if (two) *reinterpret_cast<__half2*>(p.out16 + o) = __floats2half2_rn(g0, g1);
+                                else p.out16[o] = __float2half_rn(g0);
+                            }
+                            if (p.out32) {
+                                const long o32 = zoff + (long)m * p.ld32 + (col >> 1);
+                                p.out32[o32] = g0;
+                                if (two) p.out32[o32 + 1] = g1;
+                            }
+                        }
+                    }
+                    continue;
+                }
+                // act1 (warp-uniform switch hoisted out of the element loops)
+                switch (p.act1) {
+                    case ACT_NONE: break;
+#define RVCB_ACT_CASE(A)                                                                        \
+    case A:                                                                                     \
+        _Pragma("unroll") for (int it = 0; it < NIT; ++it) {                                    \
+            t[it].x = apply_act(t[it].x, A, p.act1_p); t[it].y = apply_act(t[it].y, A, p.act1_p); \
+            t[it].z = apply_act(t[it].z, A, p.act1_p); t[it].w = apply_act(t[it].w, A, p.act1_p); \
+        }                                                                                       \
+        break;
+                    RVCB_ACT_CASE(ACT_RELU) RVCB_ACT_CASE(ACT_GELU) RVCB_ACT_CASE(ACT_LRELU) RVCB_ACT_CASE(ACT_TANH) RVCB_ACT_CASE(ACT_SIGMOID)
+#undef RVCB_ACT_CASE
+                    default: break;
+                }
+                if (p.alpha != 1.f) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) { t[it].x *= p.alpha; t[it].y *= p.alpha; t[it].z *= p.alpha; t[it].w *= p.alpha; }
+                }
+                if (p.res2) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int m = m_warp0 + rsub + RPI * it;
+                        if (m < p.M && col < p.N) {
+                            const float* r = p.res2 + zoff + (long)m * p.ldres2 + col;
+                            if (vec) {
+                                const float4 q = *reinterpret_cast<const float4*>(r);
+                                t[it].x += q.x; t[it].y += q.y; t[it].z += q.z; t[it].w += q.w;
                             } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (n0 + i < p.N) o[i] = v[i];
+                                t[it].x += r[0];
+                                if (col + 1 < p.N) t[it].y += r[1];
+                                if (col + 2 < p.N) t[it].z += r[2];
+                                if (col + 3 < p.N) t[it].w += r[3];
                             }
                         }
-                        if (p.out16) {
-                            __half* o = p.out16 + z * p.c_z + orow * p.ld16 + ocol;
-                            uint32_t pk[8];
+                    }
+                }
+                // ---- stores (coalesced: RPI rows x CW*4 bytes per warp instruction) ----
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const __half2 h2 = __floats2half2_rn(apply_act(v[2 * i], p.act2, p.act2_p),
-                                                                     apply_act(v[2 * i + 1], p.act2, p.act2_p));
-                                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                            }
-                            if (full && p.vec_ok) {
-                                *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (n0 + i < p.N)
-                                        o[i] = __ushort_as_half((unsigned short)((pk[i >> 1] >> ((i & 1) * 16)) & 0xFFFF));
-                            }
+                for (int it = 0; it < NIT; ++it) {
+                    const int m = m_warp0 + rsub + RPI * it;
+                    if (m >= p.M || col >= p.N) continue;
+                    long orow = m, ocol = col;
+                    if (p.up2_C) {
+                        const int W = p.conv2d_W, Cc = p.up2_C;
+                        const int ab = col / Cc, co = col - ab * Cc;
+                        const int ii = m / W, jj = m - ii * W;
+                        orow = (long)(2 * ii + (ab >> 1)) * (2 * W) + 2 * jj + (ab & 1);
+                        ocol = co;
+                    }
+                    if (p.out32) {
+                        float* o = p.out32 + zoff + orow * p.ld32 + ocol;
+                        if (vec) {
+                            *reinterpret_cast<float4*>(o) = t[it];
+                        } else {
+                            o[0] = t[it].x;
+                            if (col + 1 < p.N) o[1] = t[it].y;
+                            if (col + 2 < p.N) o[2] = t[it].z;
+                            if (col + 3 < p.N) o[3] = t[it].w;
+                        }
+                    }
+                    if (p.out16) {
+                        float4 u = t[it];
+                        switch (p.act2) {
+                            case ACT_NONE: break;
+                            case ACT_LRELU:
+                                u.x = u.x > 0.f ? u.x : u.x * p.act2_p; u.y = u.y > 0.f ? u.y : u.y * p.act2_p;
+                                u.z = u.z > 0.f ? u.z : u.z * p.act2_p; u.w = u.w > 0.f ? u.w : u.w * p.act2_p;
+                                break;
+                            default:
+                                u.x = apply_act(u.x, p.act2, p.act2_p); u.y = apply_act(u.y, p.act2, p.act2_p);
+                                u.z = apply_act(u.z, p.act2, p.act2_p); u.w = apply_act(u.w, p.act2, p.act2_p);
+                                break;
+                        }
+                        __half* o = p.out16 + zoff + orow * p.ld16 + ocol;
+                        if (vec) {
+                            const __half2 h0 = __floats2half2_rn(u.x, u.y), h1 = __floats2half2_rn(u.z, u.w);
+                            *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        } else {
+                            o[0] = __float2half_rn(u.x);
+                            if (col + 1 < p.N) o[1] = __float2half_rn(u.y);
+                            if (col + 2 < p.N) o[2] = __float2half_rn(u.z);
+                            if (col + 3 < p.N) o[3] = __float2half_rn(u.w);
                         }
                     }
                 }
@@ -456,9 +522,12 @@ static void encode_map(CUtensorMap* map, const void* base, int rank, const cuuin
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+struct ProfInfo { int M, N, kb, BK, BN, batch, nseg, tiles; };
+static std::vector<ProfInfo> g_prof_info;
 void gemm_prof_begin() {
     for (auto& e : g_prof_events) g_prof_pool.push_back(e);
     g_prof_events.clear();
+    g_prof_info.clear();
     g_prof_on = true;
 }
 void gemm_prof_end(double* ms_total, unsigned long long* launches) {
@@ -469,6 +538,19 @@ void gemm_prof_end(double* ms_total, unsigned long long* launches) {
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second));
         tot += ms;
+    }
+    if (const char* path = getenv("RVCB_PROF_CSV")) {
+        if (FILE* f = fopen(path, "w")) {
+            fprintf(f, "idx,M,N,kblocks,BK,BN,batch,nseg,tiles,ms,tflops\n");
+            for (size_t i = 0; i < g_prof_events.size() && i < g_prof_info.size(); ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second);
+                const ProfInfo& q = g_prof_info[i];
+                const double fl = 2.0 * q.M * q.N * (double)q.kb * q.BK * q.batch;
+                fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.2f\n", i, q.M, q.N, q.kb, q.BK, q.BN, q.batch, q.nseg, q.tiles, ms, fl / (ms * 1e-3) / 1e12);
+            }
+            fclose(f);
+        }
     }
     if (ms_total) *ms_total = tot;
     if (launches) *launches = g_prof_events.size();
@@ -508,6 +590,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
     if (g_prof_on) {
         CUDA_CHECK(cudaEventRecord(ev.second, stream));
         g_prof_events.push_back(ev);
+        g_prof_info.push_back({p.M, p.N, p.total_kb, BK, BN, p.batch, p.nseg, p.num_tiles});
     }
     count_launch();
 }
@@ -554,13 +637,13 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
     p.up2_C = g.up2_C;
     auto al = [](const void* ptr, int a) { return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % a) == 0; };
-    bool v = al(g.out32, 16) && al(g.out16, 16) && al(g.res1, 16) && al(g.res2, 16) && al(g.bias, 16);
+    bool v = al(g.out32, 16) && al(g.out16, 8) && al(g.res1, 16) && al(g.res2, 16) && al(g.bias, 16);
     if (g.out32) v = v && (g.ld32 % 4 == 0);
-    if (g.out16) v = v && (g.ld16 % 8 == 0);
+    if (g.out16) v = v && (g.ld16 % 4 == 0);
     if (g.res1) v = v && (g.ldres1 % 4 == 0);
     if (g.res2) v = v && (g.ldres2 % 4 == 0);
-    v = v && (g.c_z % 8 == 0) && (g.bias_z % 4 == 0);
-    if (g.up2_C) v = v && (g.up2_C % 16 == 0);
+    v = v && (g.c_z % 4 == 0) && (g.bias_z % 4 == 0);
+    if (g.up2_C) v = v && (g.up2_C % 4 == 0);
     p.vec_ok = v ? 1 : 0;
     if (g.bias && !g.bias_per_row) RVCB_CHECK(al(g.bias, 16) && g.bias_z % 4 == 0, "gemm: bias must be 16B aligned");
 

@@ -292,16 +292,39 @@ void add_rowvec(float* x, const float* v, int T, int C, __half* out16, float lre
 // ---------------------------------------------------------------------------------------------
 // NSF sine source
 // ---------------------------------------------------------------------------------------------
-__global__ void sine_phase_kernel(const float* __restrict__ f0, int T, int upp, float sr, float* __restrict__ phase) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double acc = 0.0;                 // torch's CPU cumsum accumulates float in double (acc_type<float,false>)
-    phase[0] = 0.f;
+// phase[t] = fmod(cumsum_{s<t} r2[s], 1): block-wide scan in double (torch's CPU cumsum accumulates float in double,
+// acc_type<float,false>; double partial sums of <= 2^13 floats in (-0.5, 0.5] round to the same float in any order)
+__global__ void __launch_bounds__(1024) sine_phase_kernel(const float* __restrict__ f0, int T, int upp, float sr, float* __restrict__ phase) {
+    __shared__ double part[1024];
+    const int tid = threadIdx.x;
+    const int per = (T + 1023) / 1024;
+    const int s0 = tid * per;
     const float a_last = (float)upp;
-    for (int t = 0; t + 1 < T; ++t) {
-        const float rad = __fmul_rn(__fdiv_rn(f0[t], sr), a_last);
-        const float r2 = fmodf(__fadd_rn(rad, 0.5f), 1.0f) - 0.5f;
-        acc += (double)r2;
-        phase[t + 1] = fmodf((float)acc, 1.0f);
+    double loc = 0.0;
+    for (int i = 0; i < per; ++i) {
+        const int t = s0 + i;
+        if (t + 1 < T) {
+            const float rad = __fmul_rn(__fdiv_rn(f0[t], sr), a_last);
+            loc += (double)(fmodf(__fadd_rn(rad, 0.5f), 1.0f) - 0.5f);
+        }
+    }
+    part[tid] = loc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {          // inclusive Hillis-Steele scan
+        double v = tid >= off ? part[tid - off] : 0.0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    double acc = tid > 0 ? part[tid - 1] : 0.0;
+    if (tid == 0) phase[0] = 0.f;
+    for (int i = 0; i < per; ++i) {
+        const int t = s0 + i;
+        if (t + 1 < T) {
+            const float rad = __fmul_rn(__fdiv_rn(f0[t], sr), a_last);
+            acc += (double)(fmodf(__fadd_rn(rad, 0.5f), 1.0f) - 0.5f);
+            phase[t + 1] = fmodf((float)acc, 1.0f);
+        }
     }
 }
 __global__ void sine_wave_kernel(const float* __restrict__ f0, const float* __restrict__ phase, int T, int upp, float sr,
@@ -320,7 +343,7 @@ __global__ void sine_wave_kernel(const float* __restrict__ f0, const float* __re
 }
 void sine_source(const float* f0, int T, int upp, int sr, const float* noise, float lin_w, float lin_b, float* phase_scratch,
                  float* har, cudaStream_t s) {
-    sine_phase_kernel<<<1, 32, 0, s>>>(f0, T, upp, (float)sr, phase_scratch);
+    sine_phase_kernel<<<1, 1024, 0, s>>>(f0, T, upp, (float)sr, phase_scratch);
     KERNEL_CHECK();
     const long n = (long)T * upp;
     sine_wave_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(f0, phase_scratch, T, upp, (float)sr, noise, lin_w, lin_b, har);
@@ -339,7 +362,7 @@ __global__ void noise_conv_kernel(float* __restrict__ x, __half* __restrict__ x1
     const long base = t * stride - pad;
     for (int j = 0; j < k; ++j) {
         const long q = base + j;
-        if (q >= 0 && q < n_har) acc = fmaf(har[q], w[c * k + j], acc);
+        if (q >= 0 && q < n_har) acc = fmaf(har[q], w[j * C + c], acc);      // w is [k, C] (coalesced across channels)
     }
     const float y = x[i] + acc;
     x[i] = y;

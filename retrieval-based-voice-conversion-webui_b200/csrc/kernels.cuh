@@ -38,7 +38,7 @@ void add_rowvec(float* x, const float* v, int T, int C, __half* out16, float lre
 // NSF source (generators.py:148-194 + nsf.py:57-61): f0 [T] -> har fp32 [T*upp]
 void sine_source(const float* f0, int T, int upp, int sr, const float* noise, float lin_w, float lin_b, float* phase_scratch,
                  float* har, cudaStream_t s);
-// x[t, c] += sum_j har[t*stride + j - pad] * w[c, j] + b[c];  x16 = lrelu(x, slope)
+// x[t, c] += sum_j har[t*stride + j - pad] * w[j, c] + b[c];  x16 = lrelu(x, slope)   (w transposed to [k, C])
 void noise_conv_add(float* x, __half* x16, const float* har, long n_har, const float* w, const float* b, int T, int C, int k,
                     int stride, int pad, float slope, cudaStream_t s);
 // linear interpolation along time (F.interpolate mode="linear", align_corners=False) of [T_in, C] -> [T_out, C]

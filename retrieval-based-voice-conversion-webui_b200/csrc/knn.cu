@@ -35,9 +35,11 @@ struct rvcb_index {
     }
 };
 
-__device__ __forceinline__ float lane_order_dist(const float4* __restrict__ q, const float4* v, int chunks) {
+template <int CH>
+__device__ __forceinline__ float lane_order_dist(const float4 (&q)[CH], const float4 (&v)[CH]) {
     float acc = 0.f;
-    for (int c = 0; c < chunks; ++c) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
         const float4 a = q[c], b = v[c];
         float d;
         d = __fsub_rn(a.x, b.x); acc = __fadd_rn(acc, __fmul_rn(d, d));
@@ -51,11 +53,12 @@ __device__ __forceinline__ float lane_order_dist(const float4* __restrict__ q, c
 }
 
 // best[q] = min over db rows of pack(dist, idx).  grid = (query tiles, db splits)
-__global__ void __launch_bounds__(256) knn_top1_kernel(const float* __restrict__ db, long long n, int d, const float* __restrict__ q, int nq,
+template <int CH>
+__global__ void __launch_bounds__(256) knn_top1_kernel(const float* __restrict__ db, long long n, const float* __restrict__ q, int nq,
                                                        unsigned long long* __restrict__ best) {
     extern __shared__ float4 qs[];                 // [QT][d/4]
-    const int chunks = d >> 7;
-    const int d4 = d >> 2;
+    constexpr int d = CH * 128;
+    constexpr int d4 = d >> 2;
     const int q0 = blockIdx.x * QT;
     const int nq_tile = min(QT, nq - q0);
     for (int i = threadIdx.x; i < QT * d4; i += blockDim.x) {
@@ -70,17 +73,15 @@ __global__ void __launch_bounds__(256) knn_top1_kernel(const float* __restrict__
     float bestd = INFINITY;
     unsigned int besti = 0xffffffffu;
     for (long long r = r0 + warp; r < r1; r += 8) {
-        float4 v[KNN_MAX_CHUNKS];
+        float4 v[CH];
         const float4* vr = reinterpret_cast<const float4*>(db + r * d);
 #pragma unroll
-        for (int c = 0; c < KNN_MAX_CHUNKS; ++c)
-            if (c < chunks) v[c] = __ldg(vr + c * 32 + lane);
+        for (int c = 0; c < CH; ++c) v[c] = __ldg(vr + c * 32 + lane);
         for (int qi = 0; qi < nq_tile; ++qi) {
-            float4 qq[KNN_MAX_CHUNKS];
+            float4 qq[CH];
 #pragma unroll
-            for (int c = 0; c < KNN_MAX_CHUNKS; ++c)
-                if (c < chunks) qq[c] = qs[qi * d4 + c * 32 + lane];
-            const float dist = lane_order_dist(qq, v, chunks);
+            for (int c = 0; c < CH; ++c) qq[c] = qs[qi * d4 + c * 32 + lane];
+            const float dist = lane_order_dist<CH>(qq, v);
             if (lane == qi && (dist < bestd || (dist == bestd && (unsigned int)r < besti))) {
                 bestd = dist;
                 besti = (unsigned int)r;
@@ -105,19 +106,18 @@ __global__ void unpack_best_kernel(const unsigned long long* __restrict__ best, 
 }
 
 // one warp per query: exact scan of the probed list, ascending top-k (ties -> lower list position)
-template <int K>
-__global__ void __launch_bounds__(256) ivf_scan_kernel(const float* __restrict__ vectors, int d, const long long* __restrict__ list_off,
+template <int K, int CH>
+__global__ void __launch_bounds__(256) ivf_scan_kernel(const float* __restrict__ vectors, const long long* __restrict__ list_off,
                                                        const long long* __restrict__ list_ids, const unsigned long long* __restrict__ best,
                                                        const float* __restrict__ q, int nq, float* __restrict__ D, long long* __restrict__ I) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * 8 + warp;
     if (qi >= nq) return;
-    const int chunks = d >> 7;
-    float4 qq[KNN_MAX_CHUNKS];
+    constexpr int d = CH * 128;
+    float4 qq[CH];
     const float4* qr = reinterpret_cast<const float4*>(q + (long)qi * d);
 #pragma unroll
-    for (int c = 0; c < KNN_MAX_CHUNKS; ++c)
-        if (c < chunks) qq[c] = qr[c * 32 + lane];
+    for (int c = 0; c < CH; ++c) qq[c] = qr[c * 32 + lane];
     float bd[K];
     long long bi[K];
 #pragma unroll
@@ -128,12 +128,11 @@ __global__ void __launch_bounds__(256) ivf_scan_kernel(const float* __restrict__
         const long long a = list_off[l], b = list_off[l + 1];
         for (long long p = a; p < b; ++p) {
             const long long id = list_ids[p];
-            float4 v[KNN_MAX_CHUNKS];
+            float4 v[CH];
             const float4* vr = reinterpret_cast<const float4*>(vectors + id * d);
 #pragma unroll
-            for (int c = 0; c < KNN_MAX_CHUNKS; ++c)
-                if (c < chunks) v[c] = __ldg(vr + c * 32 + lane);
-            const float dist = lane_order_dist(qq, v, chunks);
+            for (int c = 0; c < CH; ++c) v[c] = __ldg(vr + c * 32 + lane);
+            const float dist = lane_order_dist<CH>(qq, v);
             // sorted insert; strict '<' keeps the earlier list position first on ties.  A slot that
             // still holds the (FLT_MAX, -1) filler is always replaced.
             if (dist < bd[K - 1] || bi[K - 1] < 0) {
@@ -207,12 +206,21 @@ static void top1(const float* db, long long n, int d, const float* q, int nq, un
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     const size_t smem = (size_t)QT * d * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(knn_top1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));
-        attr = true;
+#define RVCB_TOP1(CH)                                                                                              \
+    case CH: {                                                                                                     \
+        static bool attr = false;                                                                                  \
+        if (!attr) {                                                                                               \
+            CUDA_CHECK(cudaFuncSetAttribute(knn_top1_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr = true;                                                                                           \
+        }                                                                                                          \
+        knn_top1_kernel<CH><<<dim3(qtiles, (unsigned)splits), 256, smem, st>>>(db, n, q, nq, best);                \
+        break;                                                                                                     \
     }
-    knn_top1_kernel<<<dim3(qtiles, (unsigned)splits), 256, smem, st>>>(db, n, d, q, nq, best);
+    switch (d / 128) {
+        RVCB_TOP1(1) RVCB_TOP1(2) RVCB_TOP1(3) RVCB_TOP1(4) RVCB_TOP1(6) RVCB_TOP1(8)
+        default: RVCB_CHECK(false, "knn: unsupported dimension (128, 256, 384, 512, 768, 1024)");
+    }
+#undef RVCB_TOP1
     KERNEL_CHECK();
     count_launch();
 }
@@ -256,11 +264,21 @@ int rvcb_index_search(rvcb_index* ix, const float* d_q, int nq, int k, float* d_
     ensure_ws(ix, nq);
     top1(ix->centroids, ix->nlist, ix->d, d_q, nq, ix->best, st);      // coarse quantiser, nprobe = 1
     const int grid = ceil_div(nq, 8);
-    if (k == 8) ivf_scan_kernel<8><<<grid, 256, 0, st>>>(ix->vectors, ix->d, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I);
-    else if (k == 1) ivf_scan_kernel<1><<<grid, 256, 0, st>>>(ix->vectors, ix->d, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I);
-    else if (k == 4) ivf_scan_kernel<4><<<grid, 256, 0, st>>>(ix->vectors, ix->d, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I);
-    else if (k == 16) ivf_scan_kernel<16><<<grid, 256, 0, st>>>(ix->vectors, ix->d, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I);
+#define RVCB_SCAN(K, CH) ivf_scan_kernel<K, CH><<<grid, 256, 0, st>>>(ix->vectors, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I)
+#define RVCB_SCAN_K(CH)                                                       \
+    if (k == 8) RVCB_SCAN(8, CH);                                             \
+    else if (k == 1) RVCB_SCAN(1, CH);                                        \
+    else if (k == 4) RVCB_SCAN(4, CH);                                        \
+    else if (k == 16) RVCB_SCAN(16, CH);                                      \
     else RVCB_CHECK(false, "index_search: k must be 1, 4, 8 or 16");
+    if (ix->d == 768) { RVCB_SCAN_K(6) }
+    else if (ix->d == 256) { RVCB_SCAN_K(2) }
+    else if (ix->d == 128) { RVCB_SCAN_K(1) }
+    else if (ix->d == 512) { RVCB_SCAN_K(4) }
+    else if (ix->d == 1024) { RVCB_SCAN_K(8) }
+    else RVCB_CHECK(false, "index_search: unsupported dimension");
+#undef RVCB_SCAN_K
+#undef RVCB_SCAN
     KERNEL_CHECK();
     count_launch();
     RVCB_API_END

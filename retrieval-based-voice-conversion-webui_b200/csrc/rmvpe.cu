@@ -283,77 +283,91 @@ __global__ void avgpool_kernel(const float* __restrict__ x, int H, int W, int C,
     y[i] = __float2half_rn(v);
 }
 
-// BiGRU recurrence: one 8-CTA cluster per direction, W_hh slice resident in shared memory,
-// hidden state exchanged through distributed shared memory each step.
+// BiGRU recurrence: one 8-CTA cluster per direction.  Each CTA owns 32 hidden units = 96 rows of W_hh, resident in
+// shared memory (fp32, 16B-aligned rows).  A warp owns 4 units x 3 gates; 8 lanes share one row (float4 k-slices) and
+// reduce with 3 shuffles, so a unit's r/z/n sums land in one lane that applies the gates and publishes h_t to all 8 CTAs
+// through distributed shared memory.  One split cluster barrier (arrive ... wait) per step; no block barrier.
 constexpr int GRU_H = 256, GRU_CL = 8, GRU_U = GRU_H / GRU_CL;     // 32 hidden units per CTA
+constexpr int GRU_WS = 260;                                         // smem row stride (floats)
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(256)
 gru_kernel(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ whh /*[2,768,256]*/, const float* __restrict__ bhh /*[2,768]*/,
            int T, float* __restrict__ out32 /*[T,512] or null*/, __half* __restrict__ out16 /*[T,512]*/) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int dir = blockIdx.x / GRU_CL;
-    extern __shared__ float sm[];
-    float* Wc = sm;                               // [96][257]
-    float* hbuf = Wc + 96 * 257;                  // [2][256]
-    float* gh = hbuf + 512;                       // [96]
-    float* bh = gh + 96;                          // [96]
+    extern __shared__ __align__(16) float sm[];
+    float* Wc = sm;                               // [96][260]   row = gate*32 + unit_local
+    float* hbuf = Wc + 96 * GRU_WS;               // [2][256]
     const float* Wd = whh + (size_t)dir * 768 * 256;
     for (int i = threadIdx.x; i < 96 * 256; i += blockDim.x) {
         const int row = i >> 8, k = i & 255;
         const int g = row / GRU_U, ul = row - g * GRU_U;
-        Wc[row * 257 + k] = Wd[(size_t)(g * GRU_H + rank * GRU_U + ul) * 256 + k];
-    }
-    for (int i = threadIdx.x; i < 96; i += blockDim.x) {
-        const int g = i / GRU_U, ul = i - g * GRU_U;
-        bh[i] = bhh[dir * 768 + g * GRU_H + rank * GRU_U + ul];
+        Wc[row * GRU_WS + k] = Wd[(size_t)(g * GRU_H + rank * GRU_U + ul) * 256 + k];
     }
     for (int i = threadIdx.x; i < 512; i += blockDim.x) hbuf[i] = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rsub = lane >> 3, ks = lane & 7;                      // unit within the warp, k-slice
+    const int ul = warp * 4 + rsub;                                 // local unit 0..31
+    const int unit = rank * GRU_U + ul;                             // hidden unit 0..255
+    const bool leader = (ks == 0);
+    const float b_r = bhh[dir * 768 + unit], b_z = bhh[dir * 768 + GRU_H + unit], b_n = bhh[dir * 768 + 2 * GRU_H + unit];
+    float* remote[GRU_CL];
+#pragma unroll
+    for (int cr = 0; cr < GRU_CL; ++cr) remote[cr] = cluster.map_shared_rank(hbuf, cr);
     __syncthreads();
     cluster.sync();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int cur = 0;
-    for (int step = 0; step < T; ++step) {
-        const int t = dir == 0 ? step : T - 1 - step;
-        // prefetch this step's input-projection terms (independent of the recurrence)
-        float gir = 0.f, giz = 0.f, gin = 0.f;
-        if (threadIdx.x < GRU_U) {
-            const float* g0 = gi + (size_t)t * 1536 + dir * 768 + rank * GRU_U + threadIdx.x;
-            gir = __ldg(g0); giz = __ldg(g0 + GRU_H); gin = __ldg(g0 + 2 * GRU_H);
+    int t = dir == 0 ? 0 : T - 1;
+    const int dt = dir == 0 ? 1 : -1;
+    float gir = 0.f, giz = 0.f, gin = 0.f;
+    if (leader && T > 0) {
+        const float* g0 = gi + (size_t)t * 1536 + dir * 768 + unit;
+        gir = __ldg(g0); giz = __ldg(g0 + GRU_H); gin = __ldg(g0 + 2 * GRU_H);
+    }
+    for (int step = 0; step < T; ++step, t += dt) {
+        // prefetch the NEXT step's input projection (independent of the recurrence)
+        float nr = 0.f, nz = 0.f, nn = 0.f;
+        if (leader && step + 1 < T) {
+            const float* g1 = gi + (size_t)(t + dt) * 1536 + dir * 768 + unit;
+            nr = __ldg(g1); nz = __ldg(g1 + GRU_H); nn = __ldg(g1 + 2 * GRU_H);
         }
-        const float* hc = hbuf + cur * 256;
-        float hv[8];
+        const float4* hc = reinterpret_cast<const float4*>(hbuf + cur * 256);
+        float4 hv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) hv[i] = hc[lane + 32 * i];
+        for (int i = 0; i < 8; ++i) hv[i] = hc[ks + 8 * i];
+        float sums[3];
 #pragma unroll
-        for (int r = 0; r < 12; ++r) {
-            const int row = warp * 12 + r;
-            const float* wr = Wc + row * 257;
-            float acc = 0.f;
+        for (int g = 0; g < 3; ++g) {
+            const float4* wr = reinterpret_cast<const float4*>(Wc + (g * GRU_U + ul) * GRU_WS);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc = fmaf(wr[lane + 32 * i], hv[i], acc);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) gh[row] = acc + bh[row];
-        }
-        __syncthreads();
-        if (threadIdx.x < GRU_U) {
-            const int ul = threadIdx.x;
-            const float r = 1.f / (1.f + expf(-(gir + gh[ul])));
-            const float z = 1.f / (1.f + expf(-(giz + gh[GRU_U + ul])));
-            const float n = tanhf(gin + r * gh[2 * GRU_U + ul]);
-            const float hprev = hc[rank * GRU_U + ul];
-            const float hn = (1.f - z) * n + z * hprev;
-            const int nxt = cur ^ 1;
-#pragma unroll
-            for (int cr = 0; cr < GRU_CL; ++cr) {
-                float* remote = cluster.map_shared_rank(hbuf, cr);
-                remote[nxt * 256 + rank * GRU_U + ul] = hn;
+            for (int i = 0; i < 8; ++i) {
+                const float4 w4 = wr[ks + 8 * i];
+                a0 = fmaf(w4.x, hv[i].x, a0); a1 = fmaf(w4.y, hv[i].y, a1);
+                a2 = fmaf(w4.z, hv[i].z, a2); a3 = fmaf(w4.w, hv[i].w, a3);
             }
-            const size_t o = (size_t)t * 512 + dir * 256 + rank * GRU_U + ul;
-            if (out32) out32[o] = hn;
-            out16[o] = __float2half_rn(hn);
+            float a = (a0 + a1) + (a2 + a3);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            sums[g] = a;
         }
-        cluster.sync();
+        if (leader) {
+            const float r = 1.f / (1.f + expf(-(gir + sums[0] + b_r)));
+            const float z = 1.f / (1.f + expf(-(giz + sums[1] + b_z)));
+            const float n = tanhf(gin + r * (sums[2] + b_n));
+            const float hprev = hbuf[cur * 256 + unit];
+            const float hn = (1.f - z) * n + z * hprev;
+            const int o = (cur ^ 1) * 256 + unit;
+#pragma unroll
+            for (int cr = 0; cr < GRU_CL; ++cr) remote[cr][o] = hn;
+            const size_t og = (size_t)t * 512 + dir * 256 + unit;
+            if (out32) out32[og] = hn;
+            out16[og] = __float2half_rn(hn);
+        }
+        cluster.barrier_arrive();          // release: this step's DSMEM writes
+        gir = nr; giz = nz; gin = nn;
+        cluster.barrier_wait();            // acquire: everyone's h_t is visible
         cur ^= 1;
     }
 }
@@ -552,7 +566,7 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     }
     __half* gru_out = ar.alloc<__half>((size_t)T * 512);
     {
-        const size_t smem = (96 * 257 + 512 + 96 + 96) * sizeof(float);
+        const size_t smem = (96 * GRU_WS + 512) * sizeof(float);
         static bool attr = false;
         if (!attr) {
             CUDA_CHECK(cudaFuncSetAttribute(gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

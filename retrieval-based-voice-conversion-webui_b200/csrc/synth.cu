@@ -214,7 +214,12 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
             } else {
                 S.noise_stride = 1; S.noise_pad = 0;
             }
-            S.noise_w = own.upload(nw.data);
+            {   // [C, 1, k] -> [k, C]
+                std::vector<float> nt((size_t)S.noise_k * S.cout);
+                for (int co = 0; co < S.cout; ++co)
+                    for (int j = 0; j < S.noise_k; ++j) nt[(size_t)j * S.cout + co] = nw.data[(size_t)co * S.noise_k + j];
+                S.noise_w = own.upload(nt);
+            }
             S.noise_b = own.upload(w.get("dec.noise_convs." + std::to_string(i) + ".bias").data);
             ch = S.cout;
             const int bk = ch >= 64 ? 64 : 32;

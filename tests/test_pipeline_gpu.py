@@ -73,7 +73,7 @@ def test_vc_facade_and_realtime_engine_run():
     assert upd["maximum"] == 109
     gidx = Index.from_oracle_layout(idx)
     info, (sr, wav) = vc.vc_single(0, audio, 0, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
-    assert info.startswith("Success") and sr == 48000 and wav.dtype == np.int16 and wav.shape[0] == 48000 * 3 // 2
+    assert info.startswith("Success") and sr == 48000 and wav.dtype == np.int16 and wav.shape[0] == 71040   # (2*174 frames)*480 - 2*x_pad*48000
     assert np.isfinite(wav.astype(np.float32)).all() and np.abs(wav).max() > 100
     # error convention: exceptions become the info string (modules.py:196-199)
     info, out = vc.vc_single(0, audio, 0, None, "harvest", gidx, "", 0.75, 3, 0, 0.25, 0.33)
