@@ -173,13 +173,21 @@ def main():
     n2 = torch.randn(T2 * 480, device=dev)
     from rvc_b200 import engine
 
+    side = torch.cuda.Stream(device=dev)
+
     def dev_step():
-        f0, _, _ = rmv.infer(audio_pad, 0.03)
+        # RMVPE (small GEMMs + the 16-CTA BiGRU) runs on a side stream next to HuBERT / retrieval / synthesizer
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            f0, _, _ = rmv.infer(audio_pad, 0.03)
         feats = hub.extract(audio_pad, 12)
         D, I = index.search_device(feats, 8)
         fb = index.blend_device(feats, D, I, 0.75)
         phone = engine.upsample_protect(fb, feats, pitchf, T2, 0.33)
-        return net.infer(phone, 0, pitch, pitchf, n1, n2)
+        out = net.infer(phone, 0, pitch, pitchf, n1, n2)
+        cur.wait_stream(side)
+        return out
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

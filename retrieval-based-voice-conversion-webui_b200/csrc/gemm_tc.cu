@@ -196,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kEpiWarps);
+            mbar_init(&tempty_bar[i], (BN / C::CW == 1) ? kEpiWarps / 2 : kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -280,9 +280,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int cgroup = ew >> 2;                                    // 0 / 1
         float* stg = epi_smem + ew * 32 * ST;
         const int c4 = lane % NV, rsub = lane / NV;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // single-chunk tiles (BN == CW): the two warp groups take alternate tiles (group g <-> accumulator stage g);
+        // otherwise both groups work on every tile and split its column chunks.
+        constexpr bool kAlt = (BN / CW == 1);
+        const int c_start = kAlt ? 0 : cgroup;
+        constexpr int c_step = kAlt ? 1 : 2;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+            if (kAlt && (iter & 1) != cgroup) continue;
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
             const int z = tile / tiles_per_z;
             const int rem = tile - z * tiles_per_z;
             const int mt = rem / p.num_n_tiles;
@@ -296,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const long zoff = z * p.c_z;
 
 #pragma unroll 1
-            for (int c = cgroup; c < BN / CW; c += 2) {
+            for (int c = c_start; c < BN / CW; c += c_step) {
                 const int n0 = nt * BN + c * CW;
                 if (n0 >= p.N) break;                                   // warp-uniform
                 // ---- TMEM -> registers (thread = row) ----
@@ -475,7 +482,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -610,6 +616,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     int BN = pick_bn(g.N);
     if (BK == 32 && BN > 64) BN = 64;
     if (BK == 16 && BN > 32) BN = 32;
+    // small grids: prefer narrower N tiles so more SMs share the operand streaming (each SM's L2->smem
+    // bandwidth is the bound for few-CTA launches)
+    while (BN > 32 && (long)ceil_div(g.M, BM) * ceil_div(g.N, BN) * g.batch < 96 && g.N > BN / 2) BN /= 2;
 
     KParams p{};
     p.M = g.M; p.N = g.N; p.nseg = g.nseg; p.batch = g.batch;

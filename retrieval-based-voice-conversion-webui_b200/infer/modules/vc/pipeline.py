@@ -61,23 +61,23 @@ class Pipeline(object):
         rmvpe_root = getattr(config, "rmvpe_state_dict", None) or Path(os.environ.get("rmvpe_root", "assets/rmvpe"))
         self.f0_gen = Generator(rmvpe_root, self.is_half, self.x_pad, self.device, self.window, self.sr)
         self._index_cache = {}
+        self._side = torch.cuda.Stream(device=self.device)
+        self._prefetched = None
 
     # -----------------------------------------------------------------------------------------
-    def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+    def _features(self, model, audio0, index, big_npy, index_rate, version):
+        """HuBERT features (+ IVF-Flat blend) of one chunk: (blended [T_h, C], unblended [T_h, C])"""
         feats = torch.from_numpy(np.ascontiguousarray(audio0, dtype=np.float32))
         if feats.dim() == 2:
             feats = feats.mean(-1)
         assert feats.dim() == 1, feats.dim()
         feats = feats.view(1, -1)
-        padding_mask = None          # all-False in the reference (pipeline.py:100)
-        t0 = time()
         with torch.no_grad():
-            logits = model.extract_features(source=feats.to(self.device, non_blocking=True), padding_mask=padding_mask,
+            logits = model.extract_features(source=feats.to(self.device, non_blocking=True), padding_mask=None,   # all-False, pipeline.py:100
                                             output_layer=9 if version == "v1" else 12)
             feats = model.final_proj(logits[0]) if version == "v1" else logits[0]
-        use_protect = protect < 0.5 and pitch is not None and pitchf is not None
-        feats0 = feats[0] if use_protect else None
-        f = feats[0]
+        f0 = feats[0]
+        f = f0
         if index is not None and big_npy is not None and index_rate != 0:
             if isinstance(index, engine.Index):
                 D, I = index.search_device(f, 8)                       # IVF-Flat nprobe=1, k=8 on the device
@@ -92,6 +92,20 @@ class Pipeline(object):
                 weight /= weight.sum(axis=1, keepdims=True)
                 npy = np.sum(big_npy[ix] * np.expand_dims(weight, axis=2), axis=1)
                 f = torch.from_numpy(npy.astype(np.float32)).to(self.device) * index_rate + (1 - index_rate) * f
+        return f, f0
+
+    def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+        t0 = time()
+        if self._prefetched is not None and self._prefetched[0] is audio0:
+            _, f, f_raw, ev = self._prefetched          # computed on the side stream while RMVPE was running
+            self._prefetched = None
+            torch.cuda.current_stream().wait_event(ev)
+            f.record_stream(torch.cuda.current_stream())
+            f_raw.record_stream(torch.cuda.current_stream())
+        else:
+            f, f_raw = self._features(model, audio0, index, big_npy, index_rate, version)
+        use_protect = protect < 0.5 and pitch is not None and pitchf is not None
+        feats0 = f_raw if use_protect else None
         t1 = time()
         p_len = audio0.shape[0] // self.window
         if 2 * f.shape[0] < p_len:
@@ -168,6 +182,15 @@ class Pipeline(object):
                 traceback.print_exc()
         sid = torch.tensor(sid, device=self.device).unsqueeze(0).long()
         pitch, pitchf = None, None
+        self._prefetched = None
+        if not opt_ts and if_f0 == 1:
+            # one chunk: content features + retrieval do not depend on f0 -> run them on a side stream under RMVPE
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._prefetched = (audio_pad, f, f_raw, ev)
         if if_f0:
             if if_f0 == 1:
                 pitch, pitchf = self.f0_gen.calculate(audio_pad, p_len, f0_up_key, f0_method, filter_radius, inp_f0)
@@ -187,7 +210,7 @@ class Pipeline(object):
                                      pitchf[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
                                      times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
             s = t
-        audio_opt.append(self.vc(model, net_g, sid, audio_pad[t:],
+        audio_opt.append(self.vc(model, net_g, sid, audio_pad if t is None else audio_pad[t:],
                                  (pitch[:, t // W:] if t is not None else pitch) if if_f0 else None,
                                  (pitchf[:, t // W:] if t is not None else pitchf) if if_f0 else None,
                                  times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])

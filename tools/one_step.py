@@ -28,13 +28,26 @@ n1 = torch.randn(192, T2, device=dev)
 n2 = torch.randn(T2 * 480, device=dev)
 
 
+side = torch.cuda.Stream(device=dev)
+USE_SIDE = os.environ.get("SIDE_STREAM", "1") == "1"
+
+
 def dev_step():
-    f0, _, _ = rmv.infer(audio_pad, 0.03)
+    cur = torch.cuda.current_stream()
+    if USE_SIDE:
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            f0, _, _ = rmv.infer(audio_pad, 0.03)
+    else:
+        f0, _, _ = rmv.infer(audio_pad, 0.03)
     feats = hub.extract(audio_pad, 12)
     D, I = index.search_device(feats, 8)
     fb = index.blend_device(feats, D, I, 0.75)
     phone = engine.upsample_protect(fb, feats, pitchf, T2, 0.33)
-    return net.infer(phone, 0, pitch, pitchf, n1, n2)
+    out = net.infer(phone, 0, pitch, pitchf, n1, n2)
+    if USE_SIDE:
+        cur.wait_stream(side)
+    return out
 
 
 for _ in range(3):
