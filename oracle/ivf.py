@@ -40,13 +40,46 @@ import numpy as np
 FLT_MAX = np.float32(3.4028235e38)
 
 
-def l2sqr_lane_order(q: np.ndarray, v: np.ndarray) -> np.ndarray:
+try:  # the same arithmetic, compiled and threaded over (query, vector) pairs; numpy version below is the definition
+    import numba
+
+    @numba.njit(parallel=True, cache=True, fastmath=False)
+    def _l2sqr_lane_order_nb(q, v, out):
+        nq, d = q.shape
+        nv = v.shape[0]
+        ch = d // 128
+        for i in numba.prange(nq):
+            acc = np.zeros(32, np.float32)
+            tmp = np.zeros(32, np.float32)
+            for j in range(nv):
+                for l in range(32):
+                    acc[l] = np.float32(0.0)
+                for c in range(ch):
+                    for e in range(4):
+                        for l in range(32):
+                            diff = q[i, 128 * c + 4 * l + e] - v[j, 128 * c + 4 * l + e]
+                            acc[l] = acc[l] + diff * diff
+                for s in (16, 8, 4, 2, 1):
+                    for l in range(32):
+                        tmp[l] = acc[l] + acc[l ^ s]
+                    for l in range(32):
+                        acc[l] = tmp[l]
+                out[i, j] = acc[0]
+except Exception:  # pragma: no cover
+    numba = None
+
+
+def l2sqr_lane_order(q: np.ndarray, v: np.ndarray, use_numba: bool = True) -> np.ndarray:
     """q [nq,d], v [nv,d] f32 -> [nq,nv] f32 squared L2 in the defined summation order."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     v = np.ascontiguousarray(v, dtype=np.float32)
     nq, d = q.shape
     nv = v.shape[0]
     assert d % 128 == 0
+    if use_numba and numba is not None:
+        out = np.empty((nq, nv), dtype=np.float32)
+        _l2sqr_lane_order_nb(q, v, out)
+        return out
     qc = q.reshape(nq, 1, d // 128, 32, 4)
     vc = v.reshape(1, nv, d // 128, 32, 4)
     acc = np.zeros((nq, nv, 32), dtype=np.float32)

@@ -9,147 +9,9 @@
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // Conv taps are K-segments whose A tile is the same matrix at a shifted TMA coordinate;
 // zero padding comes from TMA out-of-bounds fill, so no im2col buffer ever exists.
-#include "gemm.cuh"
-
-#include <cudaTypedefs.h>
-#include <cstdlib>
-#include <mutex>
-#include <vector>
+#include "tc_common.cuh"
 
 namespace rvcb {
-
-// ------------------------------------------------------------------------------------------------
-// kernel parameters
-// ------------------------------------------------------------------------------------------------
-struct SegPacked {
-    short row, col, nk;
-    signed char dw, pad;
-};
-
-struct KParams {
-    int M, N, nseg, batch, num_m_tiles, num_n_tiles, num_tiles, total_kb;
-    int conv2d_W, BH;
-    int a_row_z, a_col_z, b_row_z, b_col_z, b_col0;
-    long c_z, bias_z;
-    const float* bias;
-    int bias_per_row;
-    const float* res1; long ldres1;
-    const float* res2; long ldres2;
-    float alpha;
-    int act1; float act1_p;
-    int act2; float act2_p;
-    int gate;
-    float* out32; long ld32;
-    __half* out16; long ld16;
-    int up2_C;
-    int vec_ok;
-    SegPacked seg[GEMM_MAX_SEG];
-};
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_c),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100).
-//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout type
-template <int BK>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
-    constexpr uint64_t layout = (BK == 64) ? 2ull : (BK == 32) ? 4ull : 6ull;     // SW128 / SW64 / SW32
-    constexpr uint64_t sbo = (8 * BK * 2) >> 4;                                  // 8 rows of BK fp16
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// ------------------------------------------------------------------------------------------------
-// the kernel
-// ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 320;          // 2 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
-constexpr int BM = 128;
 
 template <int BN, int BK>
 struct Cfg {
@@ -496,39 +358,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    });
-    RVCB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-    return fn;
-}
-
-static CUtensorMapSwizzle swizzle_for(int bk) {
-    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-}
-
-static void encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                       const cuuint32_t* box, int bk) {
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    RVCB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
-    for (int i = 0; i < rank - 1; ++i) RVCB_CHECK(strides_bytes[i] % 16 == 0, "TMA stride must be a multiple of 16 bytes");
-    CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-}
-
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
-struct ProfInfo { int M, N, kb, BK, BN, batch, nseg, tiles; };
 static std::vector<ProfInfo> g_prof_info;
 void gemm_prof_begin() {
     for (auto& e : g_prof_events) g_prof_pool.push_back(e);
@@ -561,6 +394,18 @@ void gemm_prof_end(double* ms_total, unsigned long long* launches) {
     if (ms_total) *ms_total = tot;
     if (launches) *launches = g_prof_events.size();
 }
+bool gemm_prof_on() { return g_prof_on; }
+static std::pair<cudaEvent_t, cudaEvent_t> prof_get();
+static std::pair<cudaEvent_t, cudaEvent_t> g_prof_cur;
+void gemm_prof_record_begin(cudaStream_t stream) {
+    g_prof_cur = prof_get();
+    CUDA_CHECK(cudaEventRecord(g_prof_cur.first, stream));
+}
+void gemm_prof_record_end(cudaStream_t stream, const ProfInfo& info) {
+    CUDA_CHECK(cudaEventRecord(g_prof_cur.second, stream));
+    g_prof_events.push_back(g_prof_cur);
+    g_prof_info.push_back(info);
+}
 static std::pair<cudaEvent_t, cudaEvent_t> prof_get() {
     if (!g_prof_pool.empty()) {
         auto e = g_prof_pool.back();
@@ -586,18 +431,10 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
         configured = true;
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    std::pair<cudaEvent_t, cudaEvent_t> ev{};
-    if (g_prof_on) {
-        ev = prof_get();
-        CUDA_CHECK(cudaEventRecord(ev.first, stream));
-    }
+    if (g_prof_on) gemm_prof_record_begin(stream);
     gemm_tc_kernel<BN, BK><<<grid, kThreads, C::SMEM, stream>>>(ta, tb, p);
     KERNEL_CHECK();
-    if (g_prof_on) {
-        CUDA_CHECK(cudaEventRecord(ev.second, stream));
-        g_prof_events.push_back(ev);
-        g_prof_info.push_back({p.M, p.N, p.total_kb, BK, BN, p.batch, p.nseg, p.num_tiles});
-    }
+    if (g_prof_on) gemm_prof_record_end(stream, {p.M, p.N, p.total_kb, BK, BN, p.batch, p.nseg, p.num_tiles});
     count_launch();
 }
 
@@ -612,6 +449,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     RVCB_CHECK(g.A && g.B && g.M > 0 && g.N > 0 && g.nseg > 0 && g.nseg <= GEMM_MAX_SEG, "gemm: bad arguments");
     RVCB_CHECK(g.block_k == 64 || g.block_k == 32 || g.block_k == 16, "gemm: block_k must be 16/32/64");
     RVCB_CHECK(g.out32 || g.out16, "gemm: no output");
+    if (gemm_ws_try(g, stream)) return;          // long stride-1 convolutions: weight-stationary halo kernel
     const int BK = g.block_k;
     int BN = pick_bn(g.N);
     if (BK == 32 && BN > 64) BN = 64;

@@ -1,0 +1,410 @@
+// Weight-stationary, halo-streaming convolution kernel (tcgen05 + TMA) for the long stride-1 Conv1d layers of
+// the NSF-HiFi-GAN vocoder (rvc/layers/residuals.py:68-85, nsf.py:145-191): M = time (up to 767 040 rows),
+// N = C_out in {32, 64, 128}, K = C_in * k.
+//
+// The streaming kernel (gemm_tc.cu) re-fetches the A tile once per tap and the whole weight matrix once per M-tile;
+// those L2->SMEM bytes, not the tensor pipe, bound it on these layers.  Here instead:
+//   * each persistent CTA owns one N-slice of the output and keeps that slice of the packed weights RESIDENT in
+//     shared memory for the whole launch (loaded once by TMA);
+//   * per M-tile it streams ONE halo tile of activations per channel chunk: rows [m0 + r_min, m0 + r_max + 128),
+//     double-buffered; every tap's A operand is the same smem tile at a row-shifted UMMA descriptor
+//     (zero padding = TMA out-of-bounds fill) -- activations are read once per N-slice, not once per tap;
+//   * the epilogue warps prefetch the residual operands of their tile BEFORE waiting for the accumulator, so the
+//     HBM latency of the fp32 residual stream hides under the MMAs.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 epilogue (two groups).
+#include "tc_common.cuh"
+
+namespace rvcb {
+
+struct WSParams {
+    KParams k;              // epilogue / shape fields reused (seg[] holds the taps)
+    int rmin, HRp, nkc, n_slices, m_tiles, bo_mode;
+};
+
+template <int BN, int BK>
+struct WSCfg {
+    static constexpr int CW = BN >= 32 ? 32 : 16;
+    static constexpr int EPI_STRIDE = CW + 4;
+    static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;
+    static constexpr int B_KB_BYTES = BN * BK * 2;                 // one K block of the resident weight slice
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
+};
+
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc_shifted(uint32_t smem_addr, int bo_mode) {
+    constexpr uint64_t layout = (BK == 64) ? 2ull : (BK == 32) ? 4ull : 6ull;
+    constexpr uint64_t sbo = (8 * BK * 2) >> 4;
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+    // Measured on B200 (tests/test_gemm_gpu.py::test_conv1d_weight_stationary_halo_kernel): the UMMA swizzle is a function of
+    // the ABSOLUTE shared-memory address, so a row-shifted start needs base_offset = 0; setting (addr >> 7) & 7 gives wrong results.
+    if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+    return d;
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ WSParams wp) {
+    using C = WSCfg<BN, BK>;
+    const KParams& p = wp.k;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int total_kb = p.nseg * wp.nkc;
+    const int b_bytes = total_kb * C::B_KB_BYTES;
+    const int a_chunk = wp.HRp * BK * 2;                         // one channel chunk of the halo tile
+    const int a_buf = ((wp.nkc * a_chunk + 1023) / 1024) * 1024;
+    uint8_t* smem_b = smem;
+    uint8_t* smem_a = smem + ((b_bytes + 1023) / 1024) * 1024;
+    uint8_t* tail = smem_a + 2 * a_buf;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* b_full = bars;            // [1]
+    uint64_t* a_full = bars + 1;        // [2]
+    uint64_t* a_empty = bars + 3;       // [2]
+    uint64_t* tfull_bar = bars + 5;     // [2]
+    uint64_t* tempty_bar = bars + 7;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* epi_smem = reinterpret_cast<float*>(tail + 128);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        mbar_init(b_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], (BN / C::CW == 1) ? kEpiWarps / 2 : kEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int slice = blockIdx.x % wp.n_slices;
+    const int mt0 = blockIdx.x / wp.n_slices;
+    const int mt_step = gridDim.x / wp.n_slices;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            mbar_expect_tx(b_full, (uint32_t)b_bytes);
+            for (int kb = 0; kb < total_kb; ++kb)
+                tma_load_2d(smem_b + kb * C::B_KB_BYTES, &tmap_b, b_full, kb * BK, slice * BN);
+            int it = 0;
+            for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+                mbar_expect_tx(&a_full[buf], (uint32_t)(wp.nkc * a_chunk));
+                for (int kc = 0; kc < wp.nkc; ++kc)
+                    tma_load_3d(smem_a + buf * a_buf + kc * a_chunk, &tmap_a, &a_full[buf], kc * BK, mt * BM + wp.rmin, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            mbar_wait(b_full, 0);
+            int it = 0;
+            for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+                const int buf = it & 1, acc = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], ph ^ 1);
+                mbar_wait(&a_full[buf], ph);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + acc * BN;
+                const uint32_t a_base = smem_u32(smem_a + buf * a_buf);
+                const uint32_t b_base = smem_u32(smem_b);
+                uint32_t first = 0;
+                for (int kc = 0; kc < wp.nkc; ++kc) {
+                    for (int j = 0; j < p.nseg; ++j) {
+                        const uint32_t a_addr = a_base + kc * a_chunk + (uint32_t)(p.seg[j].row - wp.rmin) * (BK * 2);
+                        const uint32_t b_addr = b_base + (uint32_t)(j * wp.nkc + kc) * C::B_KB_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = make_desc_shifted<BK>(a_addr + k * 32, wp.bo_mode);
+                            const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
+                            umma_f16(tmem_c, da, db, idesc, first);
+                            first = 1;
+                        }
+                    }
+                }
+                umma_commit(&a_empty[buf]);       // halo buffer free once these MMAs retire
+                umma_commit(&tfull_bar[acc]);     // accumulator complete
+            }
+        }
+    } else {
+        // ======================= epilogue (8 warps, two groups) =======================
+        constexpr int CW = C::CW, ST = C::EPI_STRIDE, NV = CW / 4;
+        constexpr int RPI = 32 / NV, NIT = 32 / RPI;
+        constexpr bool kAlt = (BN / CW == 1);
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int cgroup = ew >> 2;
+        float* stg = epi_smem + ew * 32 * ST;
+        const int c4 = lane % NV, rsub = lane / NV;
+        const int c_start = kAlt ? 0 : cgroup;
+        constexpr int c_step = kAlt ? 1 : 2;
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            if (kAlt && (it & 1) != cgroup) continue;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m_warp0 = mt * BM + quarter * 32;
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            bool waited = false;
+#pragma unroll 1
+            for (int c = c_start; c < BN / CW; c += c_step) {
+                const int n0 = slice * BN + c * CW;
+                if (n0 >= p.N) break;
+                const int col = n0 + 4 * c4;
+                const bool vec = (col + 3 < p.N) && p.vec_ok;
+                // ---- prefetch the residual operands (independent of the accumulator) ----
+                float4 r1[NIT], r2[NIT];
+#pragma unroll
+                for (int i = 0; i < NIT; ++i) {
+                    r1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    r2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int m = m_warp0 + rsub + RPI * i;
+                    if (m < p.M && col < p.N) {
+                        if (p.res1) {
+                            const float* r = p.res1 + (long)m * p.ldres1 + col;
+                            if (vec) r1[i] = *reinterpret_cast<const float4*>(r);
+                            else {
+                                r1[i].x = r[0];
+                                if (col + 1 < p.N) r1[i].y = r[1];
+                                if (col + 2 < p.N) r1[i].z = r[2];
+                                if (col + 3 < p.N) r1[i].w = r[3];
+                            }
+                        }
+                        if (p.res2) {
+                            const float* r = p.res2 + (long)m * p.ldres2 + col;
+                            if (vec) r2[i] = *reinterpret_cast<const float4*>(r);
+                            else {
+                                r2[i].x = r[0];
+                                if (col + 1 < p.N) r2[i].y = r[1];
+                                if (col + 2 < p.N) r2[i].z = r[2];
+                                if (col + 3 < p.N) r2[i].w = r[3];
+                            }
+                        }
+                    }
+                }
+                if (!waited) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    waited = true;
+                }
+                // ---- TMEM -> registers (thread = row) + bias ----
+                float v[CW];
+                {
+                    uint32_t raw[16];
+                    tmem_ld16(taddr + c * CW, raw);
+                    if constexpr (CW == 32) {
+                        uint32_t raw2[16];
+                        tmem_ld16(taddr + c * CW + 16, raw2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(raw2[i]);
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                }
+                if (p.bias) {
+                    if (n0 + CW <= p.N) {
+#pragma unroll
+                        for (int i = 0; i < CW; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CW; ++i)
+                            if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < CW; i += 4)
+                    *reinterpret_cast<float4*>(stg + lane * ST + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < NIT; ++i) {
+                    const int m = m_warp0 + rsub + RPI * i;
+                    float4 t = *reinterpret_cast<const float4*>(stg + (rsub + RPI * i) * ST + 4 * c4);
+                    if (m >= p.M || col >= p.N) continue;
+                    t.x += r1[i].x; t.y += r1[i].y; t.z += r1[i].z; t.w += r1[i].w;
+                    if (p.act1 != ACT_NONE) {
+                        t.x = apply_act(t.x, p.act1, p.act1_p); t.y = apply_act(t.y, p.act1, p.act1_p);
+                        t.z = apply_act(t.z, p.act1, p.act1_p); t.w = apply_act(t.w, p.act1, p.act1_p);
+                    }
+                    t.x = fmaf(t.x, p.alpha, r2[i].x); t.y = fmaf(t.y, p.alpha, r2[i].y);
+                    t.z = fmaf(t.z, p.alpha, r2[i].z); t.w = fmaf(t.w, p.alpha, r2[i].w);
+                    if (p.out32) {
+                        float* o = p.out32 + (long)m * p.ld32 + col;
+                        if (vec) *reinterpret_cast<float4*>(o) = t;
+                        else {
+                            o[0] = t.x;
+                            if (col + 1 < p.N) o[1] = t.y;
+                            if (col + 2 < p.N) o[2] = t.z;
+                            if (col + 3 < p.N) o[3] = t.w;
+                        }
+                    }
+                    if (p.out16) {
+                        float4 u = t;
+                        if (p.act2 == ACT_LRELU) {
+                            u.x = u.x > 0.f ? u.x : u.x * p.act2_p; u.y = u.y > 0.f ? u.y : u.y * p.act2_p;
+                            u.z = u.z > 0.f ? u.z : u.z * p.act2_p; u.w = u.w > 0.f ? u.w : u.w * p.act2_p;
+                        } else if (p.act2 != ACT_NONE) {
+                            u.x = apply_act(u.x, p.act2, p.act2_p); u.y = apply_act(u.y, p.act2, p.act2_p);
+                            u.z = apply_act(u.z, p.act2, p.act2_p); u.w = apply_act(u.w, p.act2, p.act2_p);
+                        }
+                        __half* o = p.out16 + (long)m * p.ld16 + col;
+                        if (vec) {
+                            const __half2 h0 = __floats2half2_rn(u.x, u.y), h1 = __floats2half2_rn(u.z, u.w);
+                            *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        } else {
+                            o[0] = __float2half_rn(u.x);
+                            if (col + 1 < p.N) o[1] = __float2half_rn(u.y);
+                            if (col + 2 < p.N) o[2] = __float2half_rn(u.z);
+                            if (col + 3 < p.N) o[3] = __float2half_rn(u.w);
+                        }
+                    }
+                }
+            }
+            if (!waited) mbar_wait(&tfull_bar[acc], acc_phase);      // keep the barrier protocol in lock-step even with no columns
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BK>
+static void ws_launch(const CUtensorMap& ta, const CUtensorMap& tb, const WSParams& wp, int grid, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_ws_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (gemm_prof_on()) gemm_prof_record_begin(stream);
+    gemm_ws_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(ta, tb, wp);
+    KERNEL_CHECK();
+    if (gemm_prof_on())
+        gemm_prof_record_end(stream, {wp.k.M, wp.k.N, wp.k.nseg * wp.nkc, BK, -BN /*negative = WS kernel*/, 1, wp.k.nseg, wp.m_tiles * wp.n_slices});
+    count_launch();
+}
+
+static size_t ws_smem_bytes(int BN, int BK, int nseg, int nkc, int HRp) {
+    const int CW = BN >= 32 ? 32 : 16;
+    const size_t epi = (size_t)kEpiWarps * 32 * (CW + 4) * 4;
+    const size_t b = ((size_t)nseg * nkc * BN * BK * 2 + 1023) / 1024 * 1024;
+    const size_t a = ((size_t)nkc * HRp * BK * 2 + 1023) / 1024 * 1024;
+    return b + 2 * a + 128 + epi + 1024;
+}
+
+bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
+    static int mode = -1, bo_mode = 0;
+    if (mode < 0) {
+        const char* e = getenv("RVCB_WS");
+        mode = (e && e[0] == '0') ? 0 : 1;
+        const char* b = getenv("RVCB_WS_BASEOFF");
+        bo_mode = (b && b[0] == '1') ? 1 : 0;
+    }
+    if (!mode) return false;
+    // qualifying launches: plain 1-D stride-1 convolution taps over one activation matrix
+    if (g.conv2d_W != 0 || g.batch != 1 || g.nseg < 2 || g.gate || g.up2_C || g.bias_per_row) return false;
+    if (g.block_k != 64 && g.block_k != 32) return false;
+    const int BK = g.block_k, nkc = g.seg[0].nk;
+    int rmin = g.seg[0].row_off, rmax = rmin;
+    for (int s = 0; s < g.nseg; ++s) {
+        if (g.seg[s].col_off != 0 || g.seg[s].nk != nkc) return false;
+        rmin = std::min(rmin, g.seg[s].row_off);
+        rmax = std::max(rmax, g.seg[s].row_off);
+    }
+    const int span = rmax - rmin;
+    if (span > 120) return false;
+    const int HRp = round_up(BM + span, 8);
+    const int m_tiles = ceil_div(g.M, BM);
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int BN = 0;
+    for (int cand : {64, 32, 16}) {
+        if (BK == 32 && cand > 32) continue;
+        if (cand > round_up(g.N, 16)) continue;
+        if (ws_smem_bytes(cand, BK, g.nseg, nkc, HRp) <= 226 * 1024) { BN = cand; break; }
+    }
+    if (BN == 0) return false;
+    const int n_slices = ceil_div(g.N, BN);
+    if (n_slices > sms) return false;
+    const int grid = (sms / n_slices) * n_slices;
+    // the resident weights must be amortised over enough M tiles per CTA
+    if ((long)m_tiles * n_slices < 4L * grid) return false;
+    auto al = [](const void* ptr, int a) { return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % a) == 0; };
+    WSParams wp{};
+    KParams& p = wp.k;
+    p.M = g.M; p.N = g.N; p.nseg = g.nseg; p.batch = 1;
+    for (int s = 0; s < g.nseg; ++s) {
+        p.seg[s].row = (short)g.seg[s].row_off;
+        p.seg[s].col = 0;
+        p.seg[s].nk = (short)nkc;
+        p.seg[s].dw = 0;
+    }
+    p.bias = g.bias; p.res1 = g.res1; p.ldres1 = g.ldres1; p.res2 = g.res2; p.ldres2 = g.ldres2;
+    p.alpha = g.alpha; p.act1 = g.act1; p.act1_p = g.act1_p; p.act2 = g.act2; p.act2_p = g.act2_p;
+    p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
+    bool v = al(g.out32, 16) && al(g.out16, 8) && al(g.res1, 16) && al(g.res2, 16);
+    if (g.out32) v = v && (g.ld32 % 4 == 0);
+    if (g.out16) v = v && (g.ld16 % 4 == 0);
+    if (g.res1) v = v && (g.ldres1 % 4 == 0);
+    if (g.res2) v = v && (g.ldres2 % 4 == 0);
+    p.vec_ok = v ? 1 : 0;
+    if (g.bias) RVCB_CHECK(al(g.bias, 16), "gemm_ws: bias must be 16B aligned");
+    wp.rmin = rmin; wp.HRp = HRp; wp.nkc = nkc; wp.n_slices = n_slices; wp.m_tiles = m_tiles; wp.bo_mode = bo_mode;
+
+    CUtensorMap ta, tb;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.a_cols, (cuuint64_t)g.a_rows, 1};
+        cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.lda * 2 * (cuuint64_t)g.a_rows};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)HRp, 1};
+        encode_map(&ta, g.A, 3, dims, str, box, BK);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.b_cols, (cuuint64_t)g.b_rows};
+        cuuint64_t str[1] = {(cuuint64_t)g.ldb * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        encode_map(&tb, g.B, 2, dims, str, box, BK);
+    }
+    const size_t smem = ws_smem_bytes(BN, BK, g.nseg, nkc, HRp);
+#define RVCB_WS_LAUNCH(bn, bk)                                   \
+    if (BN == bn && BK == bk) {                                  \
+        ws_launch<bn, bk>(ta, tb, wp, grid, smem, stream);       \
+        return true;                                             \
+    }
+    RVCB_WS_LAUNCH(64, 64) RVCB_WS_LAUNCH(32, 64) RVCB_WS_LAUNCH(16, 64)
+    RVCB_WS_LAUNCH(32, 32) RVCB_WS_LAUNCH(16, 32)
+#undef RVCB_WS_LAUNCH
+    return false;
+}
+
+}  // namespace rvcb

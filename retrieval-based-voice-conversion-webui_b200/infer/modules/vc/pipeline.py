@@ -27,10 +27,16 @@ bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)     # pipeline.py:23
 
 
 def _rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
-    """librosa.feature.rms (center=True, zero padding) -> [1, n_frames]"""
+    """librosa.feature.rms (center=True, zero padding) -> [1, n_frames].  frame_length == 2*hop_length here
+    (pipeline.py:28-31), so every frame is two adjacent hop blocks: O(N) block sums instead of a gather."""
     pad = frame_length // 2
     yp = np.pad(y.astype(np.float32), (pad, pad), mode="constant")
     n = 1 + (len(yp) - frame_length) // hop_length
+    if frame_length == 2 * hop_length:
+        nb = n + 1
+        blocks = (yp[: nb * hop_length].astype(np.float64) ** 2).reshape(nb, hop_length).sum(axis=1)
+        power = (blocks[:-1] + blocks[1:]) / frame_length
+        return np.sqrt(power)[None, :].astype(np.float32)
     idx = np.arange(frame_length)[None, :] + hop_length * np.arange(n)[:, None]
     return np.sqrt(np.mean(np.abs(yp[idx]) ** 2, axis=1, keepdims=True)).T.astype(np.float32)
 

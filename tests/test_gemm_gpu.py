@@ -262,3 +262,36 @@ def test_gate_and_groups():
         return o
     t, s = _both(rung)
     _cmp("group tc", t, refg); _cmp("group simt", s, refg)
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,T,bk", [(64, 64, 7, 3, 60001, 64), (32, 32, 11, 5, 150000, 32), (128, 128, 3, 1, 90000, 64),
+                                                 (128, 128, 11, 5, 80000, 64), (128, 128, 7, 1, 70000, 64), (32, 1, 7, 1, 120000, 32)])
+def test_conv1d_weight_stationary_halo_kernel(cin, cout, k, dil, T, bk):
+    """Long stride-1 convolutions dispatch to the weight-stationary halo kernel (gemm_ws.cu): same contract,
+    checked against the SIMT restatement and the torch fp32 reference."""
+    _setup()
+    from gemm_cases import run_gemm, pack_conv1d
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(12)
+    x = torch.randn(T, cin, device=dev, generator=g).half()
+    w = (torch.randn(cout, cin, k, device=dev, generator=g) / math.sqrt(cin * k)).half()
+    bias = torch.randn(max(cout, 16), device=dev, generator=g)[:cout].contiguous() if cout >= 16 else None
+    res = torch.randn(T, cout, device=dev, generator=g)
+    acc = torch.randn(T, cout, device=dev, generator=g)
+    pad = (k - 1) * dil // 2
+    conv = F.conv1d(x.float().t()[None], w.float(), bias, dilation=dil, padding=pad)[0].t()
+    ref = (conv + res) / 3.0 + acc
+    B = torch.zeros(max(cout, 16), k * ((cin + bk - 1) // bk * bk), device=dev, dtype=torch.half)
+    B[:cout] = pack_conv1d(w, bk)
+    segs = [(j * dil - pad, 0, 0, (cin + bk - 1) // bk) for j in range(k)]
+
+    def run(impl):
+        o32 = torch.zeros(T, cout, device=dev)
+        o16 = torch.zeros(T, cout, device=dev, dtype=torch.half)
+        run_gemm(impl, x, B, T, cout, segs, block_k=bk, bias=bias, res1=res, res2=acc, alpha=1.0 / 3.0,
+                 act2="lrelu", act2_p=0.1, out32=o32, ld32=cout, out16=o16, ld16=cout)
+        return o32, o16
+    (t32, t16), (s32, _) = _both(run)
+    _cmp("ws32", t32, ref); _cmp("simt32", s32, ref)
+    _cmp("ws16", t16, F.leaky_relu(ref, 0.1), 4e-3)
+    _cmp("ws-vs-simt", t32, s32, 1e-4)
