@@ -40,17 +40,17 @@ import numpy as np
 FLT_MAX = np.float32(3.4028235e38)
 
 
-try:  # the same arithmetic, compiled and threaded over (query, vector) pairs; numpy version below is the definition
+try:  # the same arithmetic, compiled (serial: numba's parallel runtime fights torch's OpenMP pool); the numpy version below is the definition
     import numba
 
-    @numba.njit(parallel=True, cache=True, fastmath=False)
+    @numba.njit(cache=True, fastmath=False)
     def _l2sqr_lane_order_nb(q, v, out):
         nq, d = q.shape
         nv = v.shape[0]
         ch = d // 128
-        for i in numba.prange(nq):
-            acc = np.zeros(32, np.float32)
-            tmp = np.zeros(32, np.float32)
+        acc = np.zeros(32, np.float32)
+        tmp = np.zeros(32, np.float32)
+        for i in range(nq):
             for j in range(nv):
                 for l in range(32):
                     acc[l] = np.float32(0.0)

@@ -355,6 +355,10 @@ bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
         if (ws_smem_bytes(cand, BK, g.nseg, nkc, HRp) <= 226 * 1024) { BN = cand; break; }
     }
     if (BN == 0) return false;
+    // measured (profiles/r1d): slicing N narrower than 64 columns only pays when the whole C_in fits one chunk
+    // (one halo tile per M-tile); otherwise the streaming kernel's 128-wide tiles are faster.
+    if (BN < 64 && BN < round_up(g.N, 16) && nkc > 1) return false;
+    if (BN < 32 && g.N > 16) return false;
     const int n_slices = ceil_div(g.N, BN);
     if (n_slices > sms) return false;
     const int grid = (sms / n_slices) * n_slices;

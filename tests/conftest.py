@@ -9,3 +9,9 @@ for p in (ROOT, os.path.join(ROOT, "retrieval-based-voice-conversion-webui_b200"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_sessionstart(session):
+    # the fp32 CPU oracle runs tiny convolutions; on many-core hosts the default thread count only adds fork/join overhead
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
