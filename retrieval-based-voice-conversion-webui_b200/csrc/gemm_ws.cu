@@ -41,7 +41,12 @@ __device__ __forceinline__ uint64_t make_desc_shifted(uint32_t smem_addr, int bo
     return d;
 }
 
-template <int BN, int BK>
+// EPI: compile-time epilogue specialisation (the generic code is instruction/latency bound with only 8 epilogue warps)
+//   0  out16 = lrelu(acc + bias)                                   (resblock c1)
+//   1  y = acc + bias + res1 ; out32 = y ; out16 = lrelu(y)         (resblock c2)
+//   2  y = alpha*(acc + bias + res1) (+ res2) ; out32 = y ; (out16 = lrelu(y))   (last c2 of a resblock: 3-branch mean)
+//   3  generic contract
+template <int BN, int BK, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ WSParams wp) {
@@ -163,6 +168,73 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int n0 = slice * BN + c * CW;
                 if (n0 >= p.N) break;
                 const int col = n0 + 4 * c4;
+                if (EPI != 3 && m_warp0 + 32 <= p.M && n0 + CW <= p.N) {
+                    // ================= specialised fast path: full 32-row slab, aligned, vectorised =================
+                    float4 r1[NIT], r2[NIT];
+                    const long rbase = (long)(m_warp0 + rsub) * p.ldres1 + col;
+                    if (EPI >= 1) {
+#pragma unroll
+                        for (int i = 0; i < NIT; ++i) r1[i] = *reinterpret_cast<const float4*>(p.res1 + rbase + (long)(RPI * i) * p.ldres1);
+                    }
+                    const bool has_r2 = (EPI == 2) && p.res2 != nullptr;
+                    if (has_r2) {
+                        const long r2base = (long)(m_warp0 + rsub) * p.ldres2 + col;
+#pragma unroll
+                        for (int i = 0; i < NIT; ++i) r2[i] = *reinterpret_cast<const float4*>(p.res2 + r2base + (long)(RPI * i) * p.ldres2);
+                    }
+                    if (!waited) {
+                        mbar_wait(&tfull_bar[acc], acc_phase);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    float v[CW];
+                    {
+                        uint32_t raw[16];
+                        tmem_ld16(taddr + c * CW, raw);
+                        if constexpr (CW == 32) {
+                            uint32_t raw2[16];
+                            tmem_ld16(taddr + c * CW + 16, raw2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(raw2[i]);
+                        } else {
+                            tmem_ld_wait();
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < CW; i += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < CW; i += 4)
+                        *reinterpret_cast<float4*>(stg + lane * ST + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    __syncwarp();
+                    const float slope = p.act2_p;
+                    const bool do16 = (EPI < 2) || p.out16 != nullptr;
+#pragma unroll
+                    for (int i = 0; i < NIT; ++i) {
+                        const int m = m_warp0 + rsub + RPI * i;
+                        float4 t = *reinterpret_cast<const float4*>(stg + (rsub + RPI * i) * ST + 4 * c4);
+                        if (EPI >= 1) { t.x += r1[i].x; t.y += r1[i].y; t.z += r1[i].z; t.w += r1[i].w; }
+                        if (EPI == 2) {
+                            t.x *= p.alpha; t.y *= p.alpha; t.z *= p.alpha; t.w *= p.alpha;
+                            if (has_r2) { t.x += r2[i].x; t.y += r2[i].y; t.z += r2[i].z; t.w += r2[i].w; }
+                        }
+                        if (EPI >= 1) *reinterpret_cast<float4*>(p.out32 + (long)m * p.ld32 + col) = t;
+                        if (do16) {
+                            t.x = t.x > 0.f ? t.x : t.x * slope; t.y = t.y > 0.f ? t.y : t.y * slope;
+                            t.z = t.z > 0.f ? t.z : t.z * slope; t.w = t.w > 0.f ? t.w : t.w * slope;
+                            const __half2 h0 = __floats2half2_rn(t.x, t.y), h1 = __floats2half2_rn(t.z, t.w);
+                            *reinterpret_cast<uint2*>(p.out16 + (long)m * p.ld16 + col) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                        }
+                    }
+                    continue;
+                }
                 const bool vec = (col + 3 < p.N) && p.vec_ok;
                 // ---- prefetch the residual operands (independent of the accumulator) ----
                 float4 r1[NIT], r2[NIT];
@@ -296,15 +368,25 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BK>
-static void ws_launch(const CUtensorMap& ta, const CUtensorMap& tb, const WSParams& wp, int grid, size_t smem, cudaStream_t stream) {
+template <int BN, int BK, int EPI>
+static void ws_launch_e(const CUtensorMap& ta, const CUtensorMap& tb, const WSParams& wp, int grid, size_t smem, cudaStream_t stream) {
     static size_t configured = 0;
     if (smem > configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_ws_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_ws_kernel<BN, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    gemm_ws_kernel<BN, BK, EPI><<<grid, kThreads, smem, stream>>>(ta, tb, wp);
+}
+
+template <int BN, int BK>
+static void ws_launch(const CUtensorMap& ta, const CUtensorMap& tb, const WSParams& wp, int grid, size_t smem, cudaStream_t stream, int epi) {
     if (gemm_prof_on()) gemm_prof_record_begin(stream);
-    gemm_ws_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(ta, tb, wp);
+    switch (epi) {
+        case 0: ws_launch_e<BN, BK, 0>(ta, tb, wp, grid, smem, stream); break;
+        case 1: ws_launch_e<BN, BK, 1>(ta, tb, wp, grid, smem, stream); break;
+        case 2: ws_launch_e<BN, BK, 2>(ta, tb, wp, grid, smem, stream); break;
+        default: ws_launch_e<BN, BK, 3>(ta, tb, wp, grid, smem, stream); break;
+    }
     KERNEL_CHECK();
     if (gemm_prof_on())
         gemm_prof_record_end(stream, {wp.k.M, wp.k.N, wp.k.nseg * wp.nkc, BK, -BN /*negative = WS kernel*/, 1, wp.k.nseg, wp.m_tiles * wp.n_slices});
@@ -400,9 +482,14 @@ bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
         encode_map(&tb, g.B, 2, dims, str, box, BK);
     }
     const size_t smem = ws_smem_bytes(BN, BK, g.nseg, nkc, HRp);
+    int epi = 3;
+    const bool common = p.vec_ok && g.bias && g.act1 == ACT_NONE && (g.N % (BN >= 32 ? 32 : 16)) == 0;
+    if (common && !g.res1 && !g.res2 && !g.out32 && g.out16 && g.act2 == ACT_LRELU && g.alpha == 1.f) epi = 0;
+    else if (common && g.res1 && !g.res2 && g.out32 && g.out16 && g.act2 == ACT_LRELU && g.alpha == 1.f) epi = 1;
+    else if (common && g.res1 && g.out32 && (!g.out16 || g.act2 == ACT_LRELU)) epi = 2;
 #define RVCB_WS_LAUNCH(bn, bk)                                   \
     if (BN == bn && BK == bk) {                                  \
-        ws_launch<bn, bk>(ta, tb, wp, grid, smem, stream);       \
+        ws_launch<bn, bk>(ta, tb, wp, grid, smem, stream, epi);  \
         return true;                                             \
     }
     RVCB_WS_LAUNCH(64, 64) RVCB_WS_LAUNCH(32, 64) RVCB_WS_LAUNCH(16, 64)
