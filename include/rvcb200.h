@@ -78,6 +78,12 @@ void rvcb_index_destroy(rvcb_index* ix);
 int rvcb_upsample_protect(const float* d_feats, const float* d_feats0, int T_h, int C, const float* d_pitchf, int T,
                           float protect, float* d_out, void* stream);
 
+/* ---- output epilogue: RMS-envelope mix + peak normalisation to the int16 range, in place (change_rms pipeline.py:26-45,
+ * scaling pipeline.py:356-360).  d_wav f32[n_out] at tgt_sr; d_audio16k f32[n_in] = the (filtered) 16 kHz input;
+ * d_scratch: >= n_in/8000 + n_out/(tgt_sr/2) + 8 doubles. */
+int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio16k, int64_t n_in, float rms_mix_rate,
+                  double* d_scratch, void* stream);
+
 /* ---- RMVPE f0 -------------------------------------------------------------------------------
  * replaces: RMVPE.compute_f0 -> mel_extractor + _mel2hidden + _decode (rvc/f0/rmvpe.py:96-164). */
 int rvcb_rmvpe_create(const rvcb_weights* w, rvcb_rmvpe** out);

@@ -96,3 +96,11 @@ extern "C" int rvcb_prof_end(double* gemm_ms, unsigned long long* gemm_launches)
     rvcb::gemm_prof_end(gemm_ms, gemm_launches);
     RVCB_API_END
 }
+
+extern "C" int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio16k, int64_t n_in, float rms_mix_rate,
+                             double* d_scratch, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_wav && d_audio16k && d_scratch && n_out > 0 && n_in > 0 && tgt_sr >= 16000, "bad argument");
+    rvcb::post_mix(d_wav, n_out, tgt_sr, d_audio16k, n_in, rms_mix_rate, d_scratch, (cudaStream_t)stream);
+    RVCB_API_END
+}

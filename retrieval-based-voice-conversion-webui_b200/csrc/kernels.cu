@@ -418,6 +418,94 @@ void upsample_protect(const float* feats, const float* feats0, int T_h, int C, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// host-DSP epilogue on the device: RMS-envelope mix (change_rms, pipeline.py:26-45) + peak normalisation to the int16
+// range (pipeline.py:356-360).  rms frames = librosa.feature.rms(frame = 2*hop, center=True, zero padding).
+// ---------------------------------------------------------------------------------------------
+__global__ void block_sumsq_kernel(const float* __restrict__ x, long n, int hop, int nblocks, double* __restrict__ sums) {
+    // block b covers padded samples [b*hop, (b+1)*hop) of yp = pad(x, hop, hop)  ->  x[(b-1)*hop ... b*hop)
+    const int b = blockIdx.x;
+    double acc = 0.0;
+    const long base = (long)(b - 1) * hop;
+    for (int i = threadIdx.x; i < hop; i += blockDim.x) {
+        const long j = base + i;
+        if (j >= 0 && j < n) {
+            const float v = x[j];
+            acc += (double)v * (double)v;
+        }
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[b] = red[0];
+}
+
+__device__ __forceinline__ float rms_interp(const double* __restrict__ sums, int nf, int frame_len, long n_out, long i) {
+    // F.interpolate(mode="linear", align_corners=False) of the [nf] rms track to n_out samples
+    const float scale = (float)nf / (float)n_out;
+    float src = scale * ((float)i + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int i0 = (int)src;
+    if (i0 > nf - 1) i0 = nf - 1;
+    const int i1 = i0 + 1 < nf ? i0 + 1 : i0;
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    const float r0 = (float)sqrt((sums[i0] + sums[i0 + 1]) / frame_len);
+    const float r1 = (float)sqrt((sums[i1] + sums[i1 + 1]) / frame_len);
+    return l0 * r0 + l1 * r1;
+}
+
+__global__ void rms_mix_kernel(float* __restrict__ y, long n2, const double* __restrict__ s1, int nf1, int fl1, const double* __restrict__ s2,
+                               int nf2, int fl2, float rate, int do_mix, unsigned int* __restrict__ amax_bits) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.f;
+    if (i < n2) {
+        v = y[i];
+        if (do_mix) {
+            const float r1 = rms_interp(s1, nf1, fl1, n2, i);
+            const float r2 = fmaxf(rms_interp(s2, nf2, fl2, n2, i), 1e-6f);
+            v *= powf(r1, 1.f - rate) * powf(r2, rate - 1.f);
+            y[i] = v;
+        }
+    }
+    float a = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+    if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+}
+
+__global__ void peak_scale_kernel(float* __restrict__ y, long n, const unsigned int* __restrict__ amax_bits) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float amax = __uint_as_float(*amax_bits) / 0.99f;
+    float sc = 32768.f;
+    if (amax > 1.f) sc /= amax;
+    y[i] *= sc;
+}
+
+void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s) {
+    const int hop1 = 16000 / 2, hop2 = sr2 / 2;
+    const int nf1 = 1 + (int)(n1 / hop1), nf2 = 1 + (int)(n2 / hop2);         // 1 + (len + 2*hop - 2*hop)/hop
+    double* s1 = scratch;
+    double* s2 = scratch + (nf1 + 2);
+    unsigned int* amax = reinterpret_cast<unsigned int*>(s2 + (nf2 + 2));
+    CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
+    const int do_mix = rate != 1.f;
+    if (do_mix) {
+        block_sumsq_kernel<<<nf1 + 1, 256, 0, s>>>(x16k, n1, hop1, nf1 + 1, s1);
+        block_sumsq_kernel<<<nf2 + 1, 256, 0, s>>>(y, n2, hop2, nf2 + 1, s2);
+        KERNEL_CHECK();
+        count_launch(2);
+    }
+    rms_mix_kernel<<<(unsigned)ceil_div_l(n2, 256), 256, 0, s>>>(y, n2, s1, nf1, 2 * hop1, s2, nf2, 2 * hop2, rate, do_mix, amax);
+    peak_scale_kernel<<<(unsigned)ceil_div_l(n2, 256), 256, 0, s>>>(y, n2, amax);
+    KERNEL_CHECK();
+    count_launch(2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp32 SIMT GEMM, 64x64x16 tiles, 4x4 register blocking
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,

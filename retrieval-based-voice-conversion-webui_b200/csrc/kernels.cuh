@@ -48,6 +48,10 @@ void interp_linear_rows(const float* in, int T_in, float* out, int T_out, int C,
 void upsample_protect(const float* feats, const float* feats0, int T_h, int C, const float* pitchf, int T, float protect,
                       float* out, cudaStream_t s);
 
+// RMS-envelope mix of the converted audio with the input's envelope + peak normalisation to the int16 range, in place on y
+// (pipeline.py:26-45, 349-360).  scratch: >= (n1/8000 + n2/(sr2/2) + 8) doubles.
+void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s);
+
 // fp32 SIMT GEMM  C[M,N] = A[M,K] * B[N,K]^T  (A rows may overlap: lda < K is allowed)
 void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, cudaStream_t s);
 

@@ -101,6 +101,10 @@ class Pipeline(object):
         return f, f0
 
     def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+        """Reference signature (pipeline.py:76): returns the chunk's waveform as a host float32 array."""
+        return self._vc_dev(model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect).cpu().numpy()
+
+    def _vc_dev(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
         t0 = time()
         if self._prefetched is not None and self._prefetched[0] is audio0:
             _, f, f_raw, ev = self._prefetched          # computed on the side stream while RMVPE was running
@@ -133,7 +137,6 @@ class Pipeline(object):
                 T = phone.shape[0]
             audio1 = net_g.infer(phone.unsqueeze(0), torch.tensor([T], device=self.device), sid,
                                  pitch=None if pitch is None else pitch[:, :T], pitchf=None if pitchf is None else pitchf[:, :T])[0, 0]
-            audio1 = audio1.data.cpu().float().numpy()
         t2 = time()
         times[0] += t1 - t0
         times[2] += t2 - t1
@@ -211,21 +214,26 @@ class Pipeline(object):
         W = self.window
         for t in opt_ts:
             t = t // W * W
-            audio_opt.append(self.vc(model, net_g, sid, audio_pad[s: t + self.t_pad2 + W],
+            audio_opt.append(self._vc_dev(model, net_g, sid, audio_pad[s: t + self.t_pad2 + W],
                                      pitch[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
                                      pitchf[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
                                      times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
             s = t
-        audio_opt.append(self.vc(model, net_g, sid, audio_pad if t is None else audio_pad[t:],
+        audio_opt.append(self._vc_dev(model, net_g, sid, audio_pad if t is None else audio_pad[t:],
                                  (pitch[:, t // W:] if t is not None else pitch) if if_f0 else None,
                                  (pitchf[:, t // W:] if t is not None else pitchf) if if_f0 else None,
                                  times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
-        audio_opt = np.concatenate(audio_opt)
+        audio_dev = audio_opt[0] if len(audio_opt) == 1 else torch.cat(audio_opt)
+        if not (tgt_sr != resample_sr >= 16000):
+            # RMS-envelope mix + peak normalisation on the device (pipeline.py:349-360), then ONE D2H copy of the result
+            a16 = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(self.device, non_blocking=True)
+            audio_dev = engine.post_mix(audio_dev.contiguous(), tgt_sr, a16, rms_mix_rate)
+            return audio_dev.cpu().numpy()
+        audio_opt = audio_dev.cpu().numpy()
         if rms_mix_rate != 1:
             audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
-        if tgt_sr != resample_sr >= 16000:
-            import torchaudio          # librosa.resample (pipeline.py:351-354) is not installed; host DSP stays on the CPU
-            audio_opt = torchaudio.functional.resample(torch.from_numpy(audio_opt.astype(np.float32)), tgt_sr, resample_sr).numpy()
+        import torchaudio          # librosa.resample (pipeline.py:351-354) is not installed; this branch stays on the host
+        audio_opt = torchaudio.functional.resample(torch.from_numpy(audio_opt.astype(np.float32)), tgt_sr, resample_sr).numpy()
         audio_max = np.abs(audio_opt).max() / 0.99
         max_int16 = 32768
         if audio_max > 1:

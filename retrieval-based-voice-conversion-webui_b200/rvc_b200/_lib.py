@@ -72,6 +72,7 @@ SIGNATURES = {
     "rvcb_knn_bruteforce_top1": (_I, [_P, _L, _I, _P, _I, _P, _P, _P]),
     "rvcb_index_destroy": (None, [_P]),
     "rvcb_upsample_protect": (_I, [_P, _P, _I, _I, _P, _I, _F, _P, _P]),
+    "rvcb_post_mix": (_I, [_P, _L, _I, _P, _L, _F, _P, _P]),
     "rvcb_rmvpe_create": (_I, [_P, C.POINTER(_P)]),
     "rvcb_rmvpe_num_frames": (_I, [_I]),
     "rvcb_rmvpe_infer": (_I, [_P, _P, _I, _F, _P, _P, _P, C.POINTER(_I), _P]),

@@ -167,6 +167,15 @@ def upsample_protect(feats: torch.Tensor, feats0: Optional[torch.Tensor], pitchf
     return out
 
 
+def post_mix(wav: torch.Tensor, tgt_sr: int, audio16k: torch.Tensor, rms_mix_rate: float) -> torch.Tensor:
+    """In place on ``wav`` (device f32 [n]): RMS-envelope mix with the 16 kHz input + peak normalisation to the int16 range."""
+    wav = _chk_dev(wav.reshape(-1), torch.float32, "wav")
+    a = _chk_dev(audio16k.reshape(-1), torch.float32, "audio16k")
+    scratch = torch.empty(a.numel() // 8000 + wav.numel() // (tgt_sr // 2) + 16, device=wav.device, dtype=torch.float64)
+    _lib.check(_lib.lib().rvcb_post_mix(_p(wav), wav.numel(), int(tgt_sr), _p(a), a.numel(), float(rms_mix_rate), _p(scratch), _stream_ptr()))
+    return wav
+
+
 class Rmvpe:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0):
         _lib.init(device)

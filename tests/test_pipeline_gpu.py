@@ -86,3 +86,21 @@ def test_vc_facade_and_realtime_engine_run():
     assert y.shape == (21 * 480,) and torch.isfinite(y).all()
     y2 = rt.infer(win, 2560, 250, 21, "rmvpe", protect=0.33)
     assert y2.shape == (10080,)
+
+
+@pytest.mark.parametrize("rate", [0.25, 1.0])
+def test_post_mix_matches_reference_host_dsp(rate):
+    """Device RMS-envelope mix + peak normalisation vs the oracle's restatement of change_rms / scaling (pipeline.py:26-45, 356-360)."""
+    from oracle import pipeline as OP, weights as OW
+    from rvc_b200 import engine
+    a16 = OW.synth_voice(3.0, seed=8).numpy()
+    rng = np.random.RandomState(0)
+    env = np.repeat(rng.rand(9) * 1.5 + 0.05, 16000)[: 3 * 48000]
+    wav = (rng.randn(3 * 48000) * env).astype(np.float32)
+    ref = wav.copy()
+    if rate != 1:
+        ref = OP.change_rms(a16, 16000, ref, 48000, rate)
+    amax = np.abs(ref).max() / 0.99
+    ref = ref * (32768 / amax if amax > 1 else 32768)
+    out = engine.post_mix(torch.from_numpy(wav).cuda(), 48000, torch.from_numpy(a16).cuda(), rate).cpu().numpy()
+    assert np.abs(out - ref).max() <= 2e-3 * np.abs(ref).max()
