@@ -67,6 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // dependents may start their prologue now ...
+    pdl_wait();         // ... and nothing of ours touches global memory before the previous grids have completed
 
     const int tiles_per_z = p.num_m_tiles * p.num_n_tiles;
 
@@ -432,7 +434,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (g_prof_on) gemm_prof_record_begin(stream);
-    gemm_tc_kernel<BN, BK><<<grid, kThreads, C::SMEM, stream>>>(ta, tb, p);
+    launch_pdl(gemm_tc_kernel<BN, BK>, grid, kThreads, C::SMEM, stream, ta, tb, p);
     KERNEL_CHECK();
     if (g_prof_on) gemm_prof_record_end(stream, {p.M, p.N, p.total_kb, BK, BN, p.batch, p.nseg, p.num_tiles});
     count_launch();

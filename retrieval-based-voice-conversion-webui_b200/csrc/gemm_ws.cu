@@ -90,6 +90,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
 
     const int slice = blockIdx.x % wp.n_slices;
     const int mt0 = blockIdx.x / wp.n_slices;
@@ -375,7 +377,7 @@ static void ws_launch_e(const CUtensorMap& ta, const CUtensorMap& tb, const WSPa
         CUDA_CHECK(cudaFuncSetAttribute(gemm_ws_kernel<BN, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    gemm_ws_kernel<BN, BK, EPI><<<grid, kThreads, smem, stream>>>(ta, tb, wp);
+    launch_pdl(gemm_ws_kernel<BN, BK, EPI>, grid, kThreads, smem, stream, ta, tb, wp);
 }
 
 template <int BN, int BK>

@@ -3,6 +3,10 @@
 
 namespace rvcb {
 
+// let a PDL-launched successor (a tensor-core GEMM) run its prologue while this kernel executes; the successor still waits
+// for this grid's completion before touching global memory (griddepcontrol.wait)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -19,6 +23,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void layernorm_kernel(const float* __restrict__ x, long ldx, int rows, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, float* out32, long ld32, __half* out16, long ld16) {
+    pdl_trigger();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -93,6 +98,7 @@ __global__ void hubert_conv0_kernel(const float* __restrict__ wav, int n_samples
 
 __global__ void hubert_gn_gelu_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, __half* __restrict__ out, int T0) {
+    pdl_trigger();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)T0 * 512) return;
     const int c = (int)(idx & 511);
@@ -119,6 +125,7 @@ void hubert_conv0_gn_gelu(const float* wav, int n_samples, const float* w, const
 // ---------------------------------------------------------------------------------------------
 __global__ void softmax_kernel(const float* __restrict__ S, long lds, int T, __half* __restrict__ P, long ldp,
                                const float* __restrict__ qrel, long ldq, int win, __half* __restrict__ prel) {
+    pdl_trigger();
     extern __shared__ float row[];
     __shared__ float red[32];
     const long r = blockIdx.x;                  // h*T + i
@@ -183,6 +190,7 @@ void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, c
 // small elementwise kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2half_rn(x[i]);
 }
@@ -192,6 +200,7 @@ void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s) {
     count_launch();
 }
 __global__ void half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __half2float(x[i]);
 }
@@ -215,6 +224,7 @@ void cast_f32_f16_2d(const float* x, long ldx, __half* y, long ldy, int rows, in
 
 __global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ x, const float* __restrict__ b,
                               const float* __restrict__ add, float* __restrict__ y, int N, int K) {
+    pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -231,6 +241,7 @@ void matvec(const float* W, const float* x, const float* b, const float* add, fl
 
 __global__ void textenc_embed_kernel(const float* __restrict__ lin, const long long* __restrict__ pitch, const float* __restrict__ emb,
                                      int T, int C, float scale, float* __restrict__ o32, __half* __restrict__ o16) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)T * C) return;
     const int t = (int)(i / C), c = (int)(i - (long)t * C);
@@ -249,6 +260,7 @@ void textenc_embed(const float* lin, const long long* pitch, const float* emb_pi
 }
 
 __global__ void prior_kernel(const float* __restrict__ stats, const float* __restrict__ noise, long ldn, int T, int C, float* __restrict__ z) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)T * C) return;
     const int t = (int)(i / C), c = (int)(i - (long)t * C);
@@ -262,6 +274,7 @@ void prior_sample(const float* stats, const float* noise, long ldn, int T, int C
 }
 
 __global__ void flip_kernel(const float* __restrict__ in, float* __restrict__ out, __half* __restrict__ x0, int T, int C, int hc) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)T * C) return;
     const int t = (int)(i / C), c = (int)(i - (long)t * C);
@@ -354,6 +367,7 @@ void sine_source(const float* f0, int T, int upp, int sr, const float* noise, fl
 __global__ void noise_conv_kernel(float* __restrict__ x, __half* __restrict__ x16, const float* __restrict__ har, long n_har,
                                   const float* __restrict__ w, const float* __restrict__ b, int T, int C, int k, int stride, int pad,
                                   float slope) {
+    pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)T * C) return;
     const long t = i / C;

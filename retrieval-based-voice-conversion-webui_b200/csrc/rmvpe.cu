@@ -284,33 +284,32 @@ __global__ void avgpool_kernel(const float* __restrict__ x, int H, int W, int C,
 }
 
 // BiGRU recurrence: one 8-CTA cluster per direction.  Each CTA owns 32 hidden units = 96 rows of W_hh, resident in
-// shared memory (fp32, 16B-aligned rows).  A warp owns 4 units x 3 gates; 8 lanes share one row (float4 k-slices) and
+// REGISTERS (96 fp32 values per thread).  A warp owns 4 units x 3 gates; 8 lanes share one row (float4 k-slices) and
 // reduce with 3 shuffles, so a unit's r/z/n sums land in one lane that applies the gates and publishes h_t to all 8 CTAs
 // through distributed shared memory.  One split cluster barrier (arrive ... wait) per step; no block barrier.
 constexpr int GRU_H = 256, GRU_CL = 8, GRU_U = GRU_H / GRU_CL;     // 32 hidden units per CTA
-constexpr int GRU_WS = 260;                                         // smem row stride (floats)
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(256)
 gru_kernel(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ whh /*[2,768,256]*/, const float* __restrict__ bhh /*[2,768]*/,
            int T, float* __restrict__ out32 /*[T,512] or null*/, __half* __restrict__ out16 /*[T,512]*/) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int dir = blockIdx.x / GRU_CL;
-    extern __shared__ __align__(16) float sm[];
-    float* Wc = sm;                               // [96][260]   row = gate*32 + unit_local
-    float* hbuf = Wc + 96 * GRU_WS;               // [2][256]
+    __shared__ __align__(16) float hbuf[2 * GRU_H];      // double-buffered hidden state, written by all 8 CTAs through DSMEM
     const float* Wd = whh + (size_t)dir * 768 * 256;
-    for (int i = threadIdx.x; i < 96 * 256; i += blockDim.x) {
-        const int row = i >> 8, k = i & 255;
-        const int g = row / GRU_U, ul = row - g * GRU_U;
-        Wc[row * GRU_WS + k] = Wd[(size_t)(g * GRU_H + rank * GRU_U + ul) * 256 + k];
-    }
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) hbuf[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * GRU_H; i += blockDim.x) hbuf[i] = 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rsub = lane >> 3, ks = lane & 7;                      // unit within the warp, k-slice
     const int ul = warp * 4 + rsub;                                 // local unit 0..31
     const int unit = rank * GRU_U + ul;                             // hidden unit 0..255
     const bool leader = (ks == 0);
     const float b_r = bhh[dir * 768 + unit], b_z = bhh[dir * 768 + GRU_H + unit], b_n = bhh[dir * 768 + 2 * GRU_H + unit];
+    // this lane's slice of W_hh stays in REGISTERS for the whole sequence: 3 gates x 8 float4 (k = 4*(ks + 8i) .. +3)
+    float4 wreg[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            wreg[g][i] = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)(g * GRU_H + unit) * 256) + ks + 8 * i);
     float* remote[GRU_CL];
 #pragma unroll
     for (int cr = 0; cr < GRU_CL; ++cr) remote[cr] = cluster.map_shared_rank(hbuf, cr);
@@ -338,11 +337,10 @@ gru_kernel(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ 
         float sums[3];
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            const float4* wr = reinterpret_cast<const float4*>(Wc + (g * GRU_U + ul) * GRU_WS);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 w4 = wr[ks + 8 * i];
+                const float4 w4 = wreg[g][i];
                 a0 = fmaf(w4.x, hv[i].x, a0); a1 = fmaf(w4.y, hv[i].y, a1);
                 a2 = fmaf(w4.z, hv[i].z, a2); a3 = fmaf(w4.w, hv[i].w, a3);
             }
@@ -566,13 +564,7 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     }
     __half* gru_out = ar.alloc<__half>((size_t)T * 512);
     {
-        const size_t smem = (96 * GRU_WS + 512) * sizeof(float);
-        static bool attr = false;
-        if (!attr) {
-            CUDA_CHECK(cudaFuncSetAttribute(gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
-        gru_kernel<<<2 * GRU_CL, 256, smem, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        gru_kernel<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         KERNEL_CHECK();
         count_launch();
     }

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <cstdlib>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 namespace rvcb {
@@ -86,6 +87,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its predecessor
+// drains; pdl_wait() blocks until every prerequisite grid has completed and its memory is visible, pdl_trigger() lets the
+// next kernel in the stream begin its prologue (barrier init, TMEM alloc, descriptor prefetch) on idle SMs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,6 +181,29 @@ inline void encode_map(CUtensorMap* map, const void* base, int rank, const cuuin
     RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+
+// launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (enabled with RVCB_PDL=1)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("RVCB_PDL");
+        // measured (profiles/README.md): -0.6 ms on the serial step, neutral-to-slightly-negative when RMVPE shares the GPU on a
+        // side stream (early CTAs park on SMs the other stream could use) -> opt-in
+        use_pdl = (e && e[0] == '1') ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
 
 // per-launch profiling hooks (defined in gemm_tc.cu)
 struct ProfInfo { int M, N, kb, BK, BN, batch, nseg, tiles; };

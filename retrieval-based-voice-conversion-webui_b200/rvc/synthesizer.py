@@ -35,7 +35,7 @@ class SynthesizerB200:
         self._synth = Synth(_fold_weight_norm(cpt["weight"]), self.config, self.encoder_dim, dev.index or 0)
         self.upp = self._synth.upp
         self.inter = self._synth.inter
-        self._noise = None
+        self._noise = []
 
     # nn.Module look-alikes -------------------------------------------------------------------
     def half(self): return self
@@ -46,8 +46,8 @@ class SynthesizerB200:
 
     def set_noise(self, noise_prior: torch.Tensor, noise_src: torch.Tensor):
         """Parity hook (precedent: rvc/onnx/synthesizer.py:66-80 takes ``rnd`` as an input): the next
-        ``infer`` consumes these tensors instead of drawing randn."""
-        self._noise = (noise_prior, noise_src)
+        ``infer`` consumes these tensors instead of drawing randn (queued: one entry per upcoming ``infer`` call)."""
+        self._noise.append((noise_prior, noise_src))
 
     @torch.no_grad()
     def infer(self, phone: torch.Tensor, phone_lengths: torch.Tensor, sid: torch.Tensor, pitch: Optional[torch.Tensor] = None,
@@ -66,9 +66,8 @@ class SynthesizerB200:
         else:
             skip_head = return_length = None
             Tf, Td = T, T
-        if self._noise is not None:
-            n1, n2 = self._noise
-            self._noise = None
+        if self._noise:
+            n1, n2 = self._noise.pop(0)
         else:   # synthesizers.py:180,188 randn_like(m_p); generators.py:160,192 rand(1,1,1) + randn_like(sine_waves)
             n1 = torch.randn(1, self.inter, Tf, device=self.device)
             torch.rand(1, 1, 1, device=self.device)

@@ -1,4 +1,6 @@
 """GPU end-to-end: the drop-in Pipeline / VC / rtrvc.RVC front doors against the oracle pipeline on one utterance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -104,3 +106,60 @@ def test_post_mix_matches_reference_host_dsp(rate):
     ref = ref * (32768 / amax if amax > 1 else 32768)
     out = engine.post_mix(torch.from_numpy(wav).cuda(), 48000, torch.from_numpy(a16).cuda(), rate).cpu().numpy()
     assert np.abs(out - ref).max() <= 2e-3 * np.abs(ref).max()
+
+
+def test_pipeline_multichunk_long_audio_matches_oracle():
+    """Audio longer than x_max is cut at the quietest samples (pipeline.py:222-236) and converted chunk by chunk."""
+    from infer.modules.vc.pipeline import Pipeline
+    from infer.modules.vc.utils import HubertB200
+    from rvc.synthesizer import get_synthesizer
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(7.0, 1500)
+
+    class C2(Cfg):
+        x_pad, x_query, x_center, x_max = 1, 1, 2, 3
+    cfg = C2()
+    cfg.rmvpe_state_dict = rw
+    op = OP.OraclePipeline(48000, 1, 1, 2, 3, hw, rw, sw, OW.V2_48K_CONFIG, noise_seed=5)
+    p_len = (len(audio) + 32000) // 160
+    pitchf = (150 + 60 * np.sin(np.arange(p_len) / 30.0)).astype(np.float64)
+    pitchf[200:260] = 0
+    from oracle import rmvpe as ORM
+    pitch, _ = ORM.post_process(pitchf.copy(), 0)
+    with torch.no_grad():
+        ref = op.pipeline(0, audio.copy(), 0, (pitch, pitchf), None, 0.0, 2, 48000, 0, 1.0, "v2", 0.5)
+    assert len(op.taps) == 4                      # 3 cut points -> 4 chunks
+    pipe = Pipeline(48000, cfg)
+    net_g, _ = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
+    for tp in op.taps:
+        net_g.set_noise(*tp["noise"])
+    out = pipe.pipeline(HubertB200(hw, "cuda:0"), net_g, 0, audio.copy(), [0, 0, 0], 0, (pitch, pitchf), "", 0.0, 2, 3, 48000, 0, 1.0, "v2", 0.5)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() / 32768.0 < 2e-2
+
+
+def test_vc_single_with_index_file_and_vc_multi(tmp_path):
+    """file_index as an on-disk faiss ``IwFl`` file (read without faiss), wav files in, wav files out (modules.py:201-266)."""
+    from scipy.io import wavfile
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200 import faiss_io
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.2, 800)
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    vc.get_vc(OW.synth_cpt(1234, "v2"))
+    ipath = str(tmp_path / "added_IVF20_Flat_nprobe_1_x_v2.index")
+    faiss_io.write_index(ipath, idx)
+    indir, outdir = tmp_path / "in", tmp_path / "out"
+    indir.mkdir()
+    for i in range(2):
+        wavfile.write(str(indir / f"u{i}.wav"), 16000, (OW.synth_voice(1.2, seed=20 + i).numpy() * 32767).astype(np.int16))
+    info, out = vc.vc_single(0, str(indir / "u0.wav"), 0, None, "rmvpe", ipath, "", 0.75, 3, 0, 0.25, 0.33)
+    assert info.startswith("Success") and "Index: " + ipath in info and out[1].dtype == np.int16
+    msgs = list(vc.vc_multi(0, str(indir), str(outdir), [], 0, "rmvpe", ipath, "", 0.75, 3, 0, 0.25, 0.33, "wav"))
+    assert msgs and "Success" in msgs[-1]
+    outs = sorted(os.listdir(outdir))
+    assert outs == ["u0.wav.wav", "u1.wav.wav"]
+    sr, y = wavfile.read(str(outdir / outs[0]))
+    assert sr == 48000 and len(y) > 40000

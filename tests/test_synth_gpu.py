@@ -71,3 +71,20 @@ def test_synth_v1_40k_config():
     m = Synth(w, cfg, 256)
     out = m.infer(phone[0].cuda(), 1, pitch[0].cuda(), pitchf[0].cuda(), n1[0].cuda(), n2.reshape(-1).cuda()).cpu()
     assert (out - ref).abs().max().item() <= 1e-3
+
+
+def test_synth_realtime_formant_shift_resize():
+    """rtrvc formant shift: return_length2 != return_length -> linear resize of z and of the harmonic source (nsf.py:155-162)."""
+    from oracle import synth as OS, weights as OW
+    from rvc_b200.engine import Synth
+    cfg = OW.V2_48K_CONFIG
+    w = OW.synth_weights(1234)
+    T, skip_head, rl, rl2 = 272, 250, 21, 24
+    phone, pitch, pitchf, g = _inputs(T, seed=4)
+    n1 = torch.randn(1, 192, T - (skip_head - 24), generator=g)
+    n2 = torch.randn(1, rl * 480, 1, generator=g)
+    with torch.no_grad():
+        ref = OS.synth_infer(w, cfg, phone, torch.tensor([T]), torch.tensor([0]), pitch, pitchf, n1, n2, skip_head, rl, rl2)[0, 0]
+    out = Synth(w, cfg, 768).infer(phone[0].cuda(), 0, pitch[0].cuda(), pitchf[0].cuda(), n1[0].cuda(), n2.reshape(-1).cuda(), skip_head, rl, rl2).cpu()
+    assert out.shape == ref.shape == (rl2 * 480,)
+    assert (out - ref).abs().max().item() <= 1e-3
