@@ -145,7 +145,8 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
-    assert args.warmup >= 3 or os.environ.get("RVCB_BENCH_ALLOW_SHORT"), "timing hygiene: use --warmup >= 3"
+    if args.warmup < 3:          # timing hygiene: never fewer than 3 untimed warm-up steps (reported as run)
+        args.warmup = 3
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -199,11 +200,11 @@ def main():
 
     side = torch.cuda.Stream(device=dev)
 
-    def dev_step():
+    def dev_step(use_side=True):
         # RMVPE (small GEMMs + the 16-CTA BiGRU) runs on a side stream next to HuBERT / retrieval / synthesizer
         cur = torch.cuda.current_stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side if use_side else cur):
             f0, _, _ = rmv.infer(audio_pad, 0.03)
         feats = hub.extract(audio_pad, 12)
         D, I = index.search_device(feats, 8)
@@ -246,7 +247,7 @@ def main():
     import ctypes as C
     _lib.check(_lib.lib().rvcb_prof_begin())
     for _ in range(3):
-        dev_step()
+        dev_step(use_side=False)      # serial, so every launch's event pair times that kernel alone
     gms, gn = C.c_double(0), C.c_ulonglong(0)
     _lib.check(_lib.lib().rvcb_prof_end(C.byref(gms), C.byref(gn)))
     gemm_ms_per_step = gms.value / 3
@@ -263,14 +264,14 @@ def main():
         "data": "synthetic", "rtf_x_per_gpu": value / world / 48000.0,
         "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)",
                    "l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1},
-        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(audio.nbytes * 256000 / 160000 + 2 * 1600 * 8),
-                "d2h_bytes_per_step": int(767040 * 4 + 1601 * 4), "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
+        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(2 * 256000 * 4 + 160000 * 4 + 1598 * 12 + 8),   # audio_pad (f0 + HuBERT), audio (RMS mix), pitch/pitchf
+                "d2h_bytes_per_step": int(OUT_SAMPLES * 4 + 1601 * 4),                      # mixed + normalised waveform, f0 track "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
                 "api": "infer.modules.vc.VC.vc_single (host numpy in, host int16 out)"},
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gemm_tc_kernel<*> (all implicit-GEMM launches of one utterance)",
+                     "traffic": None, "kernel": "gemm_tc_kernel<*> + gemm_ws_kernel<*> (all tcgen05 implicit-GEMM launches of one utterance, timed serially)",
                      "launches_per_step": int(gn.value // 3), "ms_per_step": gemm_ms_per_step, "peak_source": pk_src,
                      "algorithmic_flops_per_step": ALGO_FLOPS},
     }

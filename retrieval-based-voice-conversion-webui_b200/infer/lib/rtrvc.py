@@ -34,6 +34,7 @@ class RVC:
         self.cache_pitch = torch.zeros(1024, device=self.device, dtype=torch.long)
         self.cache_pitchf = torch.zeros(1024, device=self.device, dtype=torch.float32)
         self.resample_kernel = {}
+        self._side = torch.cuda.Stream(device=self.device)
         self.f0_gen = Generator(rmvpe_state_dict or Path(os.environ.get("rmvpe_root", "assets/rmvpe")), is_half, 0, self.device,
                                 self.window, self.sr)
         self.hubert = hubert_model if hubert_model is not None else load_hubert(self.device, is_half)
@@ -63,22 +64,28 @@ class RVC:
     @torch.no_grad()
     def infer(self, input_wav: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method: Union[tuple, str],
               protect: float = 1.0) -> torch.Tensor:
-        feats = input_wav.float().to(self.device)
-        if feats.dim() == 2:
-            feats = feats.mean(-1)
-        feats = feats.view(1, -1)
-        logits = self.hubert.extract_features(source=feats, padding_mask=None, output_layer=9 if self.version == "v1" else 12)
-        feats = self.hubert.final_proj(logits[0]) if self.version == "v1" else logits[0]
-        feats = torch.cat((feats, feats[:, -1:, :]), 1)[0]                       # rtrvc.py:163
-        feats0 = feats.clone() if (protect < 0.5 and self.if_f0 == 1) else None
-        try:
-            if hasattr(self, "index") and self.index_rate > 0:
-                tail = feats[skip_head // 2:]
-                D, I = self.index.search_device(tail, 8)
-                if bool((I >= 0).all()):                                        # rtrvc.py:173
-                    feats[skip_head // 2:] = self.index.blend_device(tail, D, I, self.index_rate)
-        except Exception:
-            pass
+        wav_dev = input_wav.float().to(self.device)
+        if wav_dev.dim() == 2:
+            wav_dev = wav_dev.mean(-1)
+        # content features + retrieval do not depend on f0: run them on a side stream while RMVPE runs on the main one
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            logits = self.hubert.extract_features(source=wav_dev.view(1, -1), padding_mask=None, output_layer=9 if self.version == "v1" else 12)
+            feats = self.hubert.final_proj(logits[0]) if self.version == "v1" else logits[0]
+            feats = torch.cat((feats, feats[:, -1:, :]), 1)[0]                       # rtrvc.py:163
+            feats0 = feats.clone() if (protect < 0.5 and self.if_f0 == 1) else None
+            try:
+                if hasattr(self, "index") and self.index_rate > 0:
+                    tail = feats[skip_head // 2:]
+                    D, I = self.index.search_device(tail, 8)
+                    # rtrvc.py:173 ``if (ix >= 0).all()``: selected on the device so the host never waits for HuBERT here
+                    blended = self.index.blend_device(tail, D, I, self.index_rate)
+                    feats[skip_head // 2:] = torch.where((I >= 0).all(), blended, tail)
+            except Exception:
+                pass
+            feats_ready = torch.cuda.Event()
+            feats_ready.record(self._side)
         p_len = input_wav.shape[0] // self.window
         factor = pow(2, self.formant_shift / 12)
         return_length2 = int(np.ceil(return_length * factor))
@@ -103,6 +110,10 @@ class RVC:
             self.cache_pitchf[4 - pitch.shape[0]:] = pitchf[3:-1]
             cache_pitch = self.cache_pitch[None, -p_len:]
             cache_pitchf = self.cache_pitchf[None, -p_len:] * return_length2 / return_length
+        cur.wait_event(feats_ready)
+        feats.record_stream(cur)
+        if feats0 is not None:
+            feats0.record_stream(cur)
         use_protect = protect < 0.5 and pitch is not None and pitchf is not None and feats0 is not None
         pf = None
         if use_protect:
