@@ -251,6 +251,9 @@ def main():
     gms, gn = C.c_double(0), C.c_ulonglong(0)
     _lib.check(_lib.lib().rvcb_prof_end(C.byref(gms), C.byref(gn)))
     gemm_ms_per_step = gms.value / 3
+    cls = [(C.c_double * 2)() for _ in range(4)]
+    _lib.check(_lib.lib().rvcb_prof_classes(*cls))
+    ws_ms, ws_n, ws_flops, ws_bytes = cls[0][1] / 3, cls[1][1] / 3, cls[2][1] / 3, cls[3][1] / 3
     pk, pk_src = peaks()
     achieved = ALGO_FLOPS / (gemm_ms_per_step * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
@@ -270,7 +273,15 @@ def main():
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        # dominant kernel by work: the weight-stationary vocoder convolution (44 % of the utterance's FLOPs); it is HBM-bound
+        # in this unfused layer-by-layer design: algorithmic bytes = activations in + weights + fp32 residual in + outputs
+        "roofline": {"bound": "hbm", "achieved": ws_bytes / (ws_ms * 1e-3) / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": ws_bytes / (ws_ms * 1e-3) / 1e9 / pk.get("hbm_gbs"),
+                     "traffic": 251.2e6, "traffic_note": "dram read+write of one stage-2 c2 launch (ncu --set full, profiles/prof_r1e_ws_metrics.txt) vs 294 MB algorithmic",
+                     "kernel": "gemm_ws_kernel<*> (vocoder resblock convolutions, stages 1-3 + conv_post)", "launches_per_step": ws_n,
+                     "avg_launch_us": ws_ms / max(ws_n, 1) * 1e3, "algorithmic_bytes_per_step": ws_bytes, "peak_source": pk_src,
+                     "tensor_view": {"achieved_tflops": ws_flops / (ws_ms * 1e-3) / 1e12, "frac_of_bf16_sustained": ws_flops / (ws_ms * 1e-3) / 1e12 / peak}},
+        "roofline_all_gemm": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "gemm_tc_kernel<*> + gemm_ws_kernel<*> (all tcgen05 implicit-GEMM launches of one utterance, timed serially)",
                      "launches_per_step": int(gn.value // 3), "ms_per_step": gemm_ms_per_step, "peak_source": pk_src,
                      "algorithmic_flops_per_step": ALGO_FLOPS},

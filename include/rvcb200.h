@@ -35,6 +35,9 @@ const char* rvcb_version(void);
 /* per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline); begin resets, end syncs and sums */
 int rvcb_prof_begin(void);
 int rvcb_prof_end(double* gemm_ms, unsigned long long* gemm_launches);
+/* per-kernel-class totals of the last profiled region; each array has 2 entries: [0] streaming gemm_tc_kernel, [1] weight-stationary
+ * gemm_ws_kernel (ms, launches, 2*M*N*K flops incl. K padding, algorithmic HBM bytes (WS only)) */
+int rvcb_prof_classes(double* ms2, double* launches2, double* flops2, double* bytes2);
 
 /* ---- weight container (host fp32 tensors keyed by the reference's state_dict names) ------
  * replaces: torch.load + load_state_dict in rvc/synthesizer.py:10-35, rvc/f0/models.py:9-11,

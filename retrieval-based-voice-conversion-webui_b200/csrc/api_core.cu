@@ -104,3 +104,10 @@ extern "C" int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const floa
     rvcb::post_mix(d_wav, n_out, tgt_sr, d_audio16k, n_in, rms_mix_rate, d_scratch, (cudaStream_t)stream);
     RVCB_API_END
 }
+
+extern "C" int rvcb_prof_classes(double* ms2, double* launches2, double* flops2, double* bytes2) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(ms2 && launches2 && flops2 && bytes2, "null argument");
+    rvcb::gemm_prof_classes(ms2, launches2, flops2, bytes2);
+    RVCB_API_END
+}

@@ -390,8 +390,16 @@ static void ws_launch(const CUtensorMap& ta, const CUtensorMap& tb, const WSPara
         default: ws_launch_e<BN, BK, 3>(ta, tb, wp, grid, smem, stream); break;
     }
     KERNEL_CHECK();
-    if (gemm_prof_on())
-        gemm_prof_record_end(stream, {wp.k.M, wp.k.N, wp.k.nseg * wp.nkc, BK, -BN /*negative = WS kernel*/, 1, wp.k.nseg, wp.m_tiles * wp.n_slices});
+    if (gemm_prof_on()) {
+        // algorithmic HBM bytes of this launch: activations in once, weights once, residual(s) in, outputs out
+        const KParams& q = wp.k;
+        const double mn = (double)q.M * q.N;
+        const double bytes = (double)q.M * wp.nkc * BK * 2 + (double)q.N * q.nseg * wp.nkc * BK * 2 + (q.res1 ? mn * 4 : 0) +
+                             (q.res2 ? mn * 4 : 0) + (q.out32 ? mn * 4 : 0) + (q.out16 ? mn * 2 : 0);
+        ProfInfo info{q.M, q.N, q.nseg * wp.nkc, BK, -BN /*negative = WS kernel*/, 1, q.nseg, wp.m_tiles * wp.n_slices};
+        info.bytes = bytes;
+        gemm_prof_record_end(stream, info);
+    }
     count_launch();
 }
 

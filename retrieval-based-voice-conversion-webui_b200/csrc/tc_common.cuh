@@ -206,7 +206,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
 }
 
 // per-launch profiling hooks (defined in gemm_tc.cu)
-struct ProfInfo { int M, N, kb, BK, BN, batch, nseg, tiles; };
+struct ProfInfo { int M, N, kb, BK, BN, batch, nseg, tiles; double bytes = 0; };   // bytes: algorithmic HBM bytes (WS kernel)
 bool gemm_prof_on();
 void gemm_prof_record_begin(cudaStream_t stream);
 void gemm_prof_record_end(cudaStream_t stream, const ProfInfo& info);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "rvcb_version": (C.c_char_p, []),
     "rvcb_prof_begin": (_I, []),
     "rvcb_prof_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "rvcb_prof_classes": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rvcb_weights_create": (_I, [C.POINTER(_P)]),
     "rvcb_weights_add": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
     "rvcb_weights_destroy": (None, [_P]),
