@@ -268,7 +268,8 @@ def main():
         "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)",
                    "l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1},
         "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(2 * 256000 * 4 + 160000 * 4 + 1598 * 12 + 8),   # audio_pad (f0 + HuBERT), audio (RMS mix), pitch/pitchf
-                "d2h_bytes_per_step": int(OUT_SAMPLES * 4 + 1601 * 4),                      # mixed + normalised waveform, f0 track "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
+                "d2h_bytes_per_step": int(OUT_SAMPLES * 4 + 1601 * 4),                      # mixed + normalised waveform, f0 track
+                "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0, "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
                 "api": "infer.modules.vc.VC.vc_single (host numpy in, host int16 out)"},
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
