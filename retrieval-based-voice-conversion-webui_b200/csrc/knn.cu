@@ -16,7 +16,7 @@
 
 using namespace rvcb;
 
-constexpr int KNN_MAX_CHUNKS = 8;       // d <= 1024
+
 constexpr int QT = 32;                  // queries per tile
 constexpr float KNN_FLT_MAX = 3.4028235e38f;
 
@@ -193,7 +193,7 @@ __global__ void blend_kernel(const float* __restrict__ vectors, long long ntotal
 }
 
 static void top1(const float* db, long long n, int d, const float* q, int nq, unsigned long long* best, cudaStream_t st) {
-    RVCB_CHECK(d % 128 == 0 && d <= 128 * KNN_MAX_CHUNKS, "knn: d must be a multiple of 128 and <= 1024");
+    RVCB_CHECK(d % 128 == 0 && d <= 1024, "knn: d must be a multiple of 128 and <= 1024");
     RVCB_CHECK(n < 0xffffffffLL, "knn: database too large");
     CUDA_CHECK(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * nq, st));
     const int qtiles = ceil_div(nq, QT);
