@@ -150,14 +150,15 @@ def sine_source(w: W, f0: torch.Tensor, upp: int, sr: int, noise: torch.Tensor):
 def nsf_generator(w: W, x, f0, g, noise, up_rates: List[int], up_k: List[int], rb_k: List[int],
                   rb_d: List[List[int]], sr: int, n_res: Optional[int] = None, taps: Optional[dict] = None):
     upp = math.prod(up_rates)
-    har = sine_source(w, f0, upp, sr, noise)
+    use_f0 = f0 is not None and "dec.noise_convs.0.weight" in w      # else: plain Generator (generators.py:84-113)
+    har = sine_source(w, f0, upp, sr, noise) if use_f0 else None
     if n_res is not None:
         n_res = int(n_res)
-        if n_res * upp != har.shape[-1]:
+        if use_f0 and n_res * upp != har.shape[-1]:
             har = F.interpolate(har, size=n_res * upp, mode="linear")
         if n_res != x.shape[-1]:
             x = F.interpolate(x, size=n_res, mode="linear")
-    if taps is not None:
+    if taps is not None and use_f0:
         taps["har"] = har
     x = F.conv1d(x, w["dec.conv_pre.weight"], w["dec.conv_pre.bias"], padding=3)
     x = x + F.conv1d(g, w["dec.cond.weight"], w["dec.cond.bias"])
@@ -165,12 +166,13 @@ def nsf_generator(w: W, x, f0, g, noise, up_rates: List[int], up_k: List[int], r
     for i, (u, k) in enumerate(zip(up_rates, up_k)):
         x = F.leaky_relu(x, 0.1)
         x = F.conv_transpose1d(x, w[f"dec.ups.{i}.weight"], w[f"dec.ups.{i}.bias"], stride=u, padding=(k - u) // 2)
-        if i + 1 < len(up_rates):
-            s = math.prod(up_rates[i + 1:])
-            xs_ = F.conv1d(har, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"], stride=s, padding=s // 2)
-        else:
-            xs_ = F.conv1d(har, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"])
-        x = x + xs_
+        if use_f0:
+            if i + 1 < len(up_rates):
+                s = math.prod(up_rates[i + 1:])
+                xs_ = F.conv1d(har, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"], stride=s, padding=s // 2)
+            else:
+                xs_ = F.conv1d(har, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"])
+            x = x + xs_
         acc = None
         for j in range(nk):
             r = i * nk + j
@@ -211,7 +213,8 @@ def synth_infer(w: W, config: List, phone, phone_lengths, sid, pitch, pitchf, no
         z = flow_reverse(w, z_p, mask, g, hidden)
         z = z[:, :, dec_head:dec_head + length]
         mask = mask[:, :, dec_head:dec_head + length]
-        pitchf = pitchf[:, head:head + length]
+        if pitchf is not None:
+            pitchf = pitchf[:, head:head + length]
     else:
         m_p, logs_p, mask = text_encoder(w, phone, pitch, phone_lengths, n_heads, n_layers, ksz)
         z_p = (m_p + torch.exp(logs_p) * noise_prior * 0.66666) * mask

@@ -199,6 +199,18 @@ void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s) {
     KERNEL_CHECK();
     count_launch();
 }
+__global__ void lrelu_cast_kernel(const float* __restrict__ x, __half* __restrict__ y, long n, float slope) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = x[i];
+        y[i] = __float2half_rn(v > 0.f ? v : v * slope);
+    }
+}
+void lrelu_cast(const float* x, __half* y, long n, float slope, cudaStream_t s) {
+    lrelu_cast_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(x, y, n, slope);
+    KERNEL_CHECK();
+    count_launch();
+}
 __global__ void half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
     pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;

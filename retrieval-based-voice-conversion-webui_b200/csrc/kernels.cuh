@@ -19,6 +19,7 @@ void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, c
 
 void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s);
 void half_to_float(const __half* x, float* y, long n, cudaStream_t s);   // exact widening
+void lrelu_cast(const float* x, __half* y, long n, float slope, cudaStream_t s);   // y = (half) leaky_relu(x)
 // y[r, c] = x[r, c] for a [rows, cols] fp32 matrix with leading dims -> fp16
 void cast_f32_f16_2d(const float* x, long ldx, __half* y, long ldy, int rows, int cols, cudaStream_t s);
 

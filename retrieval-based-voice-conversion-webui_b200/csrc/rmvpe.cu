@@ -370,6 +370,126 @@ gru_kernel(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ 
     }
 }
 
+// ---- v2 recurrence: same ownership (8-CTA cluster per direction, W_hh in registers), but h_t is published with
+// st.async (remote shared-memory store that completes a transaction count on the DESTINATION CTA's mbarrier), so a step
+// costs one DSMEM store latency + one mbarrier wake-up instead of a full release/acquire cluster barrier (which also has
+// to drain the step's global stores and flushes L1).  Every lane of a unit group evaluates the gates redundantly; lane
+// j < 8 of each warp then sends the warp's 4 consecutive h values as one float4 to CTA j -> one store instruction per
+// warp per step.  Two mbarriers (one per h buffer) keep step t+1 and t+2 transactions apart; each expects 1024 B/step.
+__device__ __forceinline__ uint32_t gru_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gru_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void gru_st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 :: "r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void gru_bar_arm(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gru_bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GRU_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GRU_DONE_%=;\n\t"
+        "bra GRU_WAIT_%=;\n\t"
+        "GRU_DONE_%=:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(256)
+gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ whh /*[2,768,256]*/, const float* __restrict__ bhh /*[2,768]*/,
+              int T, float* __restrict__ out32 /*[T,512] or null*/, __half* __restrict__ out16 /*[T,512]*/) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int dir = blockIdx.x / GRU_CL;
+    __shared__ __align__(16) float hbuf[2 * GRU_H];      // h_s lives in hbuf[(s & 1) * 256 ...]
+    __shared__ __align__(8) uint64_t hbar[2];            // hbar[b] completes when all 256 values of buffer b arrived
+    const float* Wd = whh + (size_t)dir * 768 * 256;
+    for (int i = threadIdx.x; i < 2 * GRU_H; i += blockDim.x) hbuf[i] = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rsub = lane >> 3, ks = lane & 7;
+    const int ul = warp * 4 + rsub;
+    const int unit = rank * GRU_U + ul;
+    const float b_r = bhh[dir * 768 + unit], b_z = bhh[dir * 768 + GRU_H + unit], b_n = bhh[dir * 768 + 2 * GRU_H + unit];
+    float4 wreg[3][8];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            wreg[g][i] = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)(g * GRU_H + unit) * 256) + ks + 8 * i);
+    const uint32_t bar0 = gru_smem_u32(&hbar[0]);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        gru_bar_arm(bar0 + 8, GRU_H * 4);      // h_1 -> buffer 1
+        gru_bar_arm(bar0, GRU_H * 4);          // h_2 -> buffer 0
+    }
+    // lane j < 8 publishes this warp's float4 (units rank*32 + warp*4 .. +3) to CTA j
+    const uint32_t dst_h = gru_mapa(gru_smem_u32(hbuf) + (uint32_t)(rank * GRU_U + warp * 4) * 4u, (uint32_t)(lane & 7));
+    const uint32_t dst_b = gru_mapa(bar0, (uint32_t)(lane & 7));
+    __syncthreads();
+    cluster.sync();
+    int t = dir == 0 ? 0 : T - 1;
+    const int dt = dir == 0 ? 1 : -1;
+    float gir = 0.f, giz = 0.f, gin = 0.f;
+    if (T > 0) {
+        const float* g0 = gi + (size_t)t * 1536 + dir * 768 + unit;
+        gir = __ldg(g0); giz = __ldg(g0 + GRU_H); gin = __ldg(g0 + 2 * GRU_H);
+    }
+    for (int s = 0; s < T; ++s, t += dt) {
+        float nr = 0.f, nz = 0.f, nn = 0.f;
+        if (s + 1 < T) {
+            const float* g1 = gi + (size_t)(t + dt) * 1536 + dir * 768 + unit;
+            nr = __ldg(g1); nz = __ldg(g1 + GRU_H); nn = __ldg(g1 + 2 * GRU_H);
+        }
+        const int cur = s & 1;
+        if (s > 0) {
+            gru_bar_wait(bar0 + 8u * cur, (uint32_t)(((s - 1) >> 1) & 1));
+            if (threadIdx.x == 0 && s + 2 <= T) gru_bar_arm(bar0 + 8u * cur, GRU_H * 4);      // for h_{s+2}
+        }
+        const float4* hc = reinterpret_cast<const float4*>(hbuf + cur * 256);
+        float4 hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hv[i] = hc[ks + 8 * i];
+        const float hprev = hbuf[cur * 256 + unit];
+        float sums[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w4 = wreg[g][i];
+                a0 = fmaf(w4.x, hv[i].x, a0); a1 = fmaf(w4.y, hv[i].y, a1);
+                a2 = fmaf(w4.z, hv[i].z, a2); a3 = fmaf(w4.w, hv[i].w, a3);
+            }
+            float a = (a0 + a1) + (a2 + a3);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            sums[g] = a;
+        }
+        const float r = 1.f / (1.f + expf(-(gir + sums[0] + b_r)));
+        const float z = 1.f / (1.f + expf(-(giz + sums[1] + b_z)));
+        const float n = tanhf(gin + r * (sums[2] + b_n));
+        const float hn = (1.f - z) * n + z * hprev;
+        const float h0 = __shfl_sync(0xffffffffu, hn, 0), h1 = __shfl_sync(0xffffffffu, hn, 8);
+        const float h2 = __shfl_sync(0xffffffffu, hn, 16), h3 = __shfl_sync(0xffffffffu, hn, 24);
+        if (s + 1 < T && lane < GRU_CL)
+            gru_st_async_v4(dst_h + (uint32_t)((cur ^ 1) * 256) * 4u, h0, h1, h2, h3, dst_b + 8u * (cur ^ 1));
+        if (ks == 0) {
+            const size_t og = (size_t)t * 512 + dir * 256 + unit;
+            if (out32) out32[og] = hn;
+            out16[og] = __float2half_rn(hn);
+        }
+        gir = nr; giz = nz; gin = nn;
+    }
+    cluster.sync();      // nobody exits while a peer may still be storing into its shared memory
+}
+
 // salience [T,360] -> f0 [T]  (rmvpe.py:119-137,157-164); one warp per frame
 __global__ void decode_kernel(const float* __restrict__ sal, int T, float thred, float* __restrict__ f0) {
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -564,7 +684,9 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     }
     __half* gru_out = ar.alloc<__half>((size_t)T * 512);
     {
-        gru_kernel<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        static const bool v1 = [] { const char* e = getenv("RVCB_GRU"); return e && !strcmp(e, "barrier"); }();
+        if (v1) gru_kernel<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        else gru_kernel_v2<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         KERNEL_CHECK();
         count_launch();
     }

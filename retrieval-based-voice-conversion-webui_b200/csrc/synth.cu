@@ -50,6 +50,7 @@ struct rvcb_synth {
     DevOwner own;
     Arena arena;
     int upp = 1, kc = 0, HP = 0;
+    bool use_f0 = true;      // false: SynthesizerTrnMs*NSFsid_nono (no pitch embedding, plain Generator decoder)
     // enc_p
     PackedB emb_phone; float* emb_phone_b = nullptr; float* emb_pitch = nullptr;
     std::vector<AttnLayer> attn;
@@ -82,7 +83,8 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
         // ---- enc_p ----
         h->emb_phone = pack_linear(own, w.get("enc_p.emb_phone.weight").data.data(), H, c.encoder_dim);
         h->emb_phone_b = own.upload(w.get("enc_p.emb_phone.bias").data);
-        h->emb_pitch = own.upload(w.get("enc_p.emb_pitch.weight").data);
+        h->use_f0 = w.has("enc_p.emb_pitch.weight");
+        if (h->use_f0) h->emb_pitch = own.upload(w.get("enc_p.emb_pitch.weight").data);
         for (int l = 0; l < c.n_layers; ++l) {
             const std::string p = "enc_p.encoder.attn_layers." + std::to_string(l) + ".";
             AttnLayer L{};
@@ -184,8 +186,10 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
         h->in_b = own.upload(inb);
         h->emb_g = own.upload(w.get("emb_g.weight").data);
         // ---- dec ----
-        h->lin_w = w.get("dec.m_source.l_linear.weight").data[0];
-        h->lin_b = w.get("dec.m_source.l_linear.bias").data[0];
+        if (h->use_f0) {
+            h->lin_w = w.get("dec.m_source.l_linear.weight").data[0];
+            h->lin_b = w.get("dec.m_source.l_linear.bias").data[0];
+        }
         const int C0 = c.upsample_initial_channel;
         h->conv_pre = pack_conv1d(own, w.get("dec.conv_pre.weight").data.data(), C0, I, 7);
         h->conv_pre_b = own.upload(w.get("dec.conv_pre.bias").data);
@@ -204,6 +208,7 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
             for (int r = 0; r < S.s; ++r)
                 for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co];
             S.up_b = own.upload(ub);
+            if (h->use_f0) {
             const WT& nw = w.get("dec.noise_convs." + std::to_string(i) + ".weight");
             S.noise_k = (int)nw.dim(2);
             if (i + 1 < c.n_upsamples) {
@@ -221,6 +226,7 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
                 S.noise_w = own.upload(nt);
             }
             S.noise_b = own.upload(w.get("dec.noise_convs." + std::to_string(i) + ".bias").data);
+            }
             ch = S.cout;
             const int bk = ch >= 64 ? 64 : 32;
             RVCB_CHECK(ch % 32 == 0, "synth: decoder channels must be multiples of 32");
@@ -301,7 +307,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
         g.bias = h->emb_phone_b; g.out32 = lin32; g.ld32 = H;
         gemm(g, st);
     }
-    textenc_embed(lin32, d_pitch, h->emb_pitch, T, H, sqrtf((float)H), x32, x16, st);
+    textenc_embed(lin32, h->use_f0 ? d_pitch : nullptr, h->emb_pitch, T, H, sqrtf((float)H), x32, x16, st);
     const int NQK = 2 * heads * HP;
     __half* qk16 = ar.alloc<__half>((size_t)T * NQK);
     __half* vT16 = ar.alloc<__half>((size_t)H * Tp);
@@ -447,15 +453,20 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     }
     const float* z = zin + (size_t)dec_head * I;          // [Td, I]
     // ================= NSF-HiFi-GAN (nsf.py:145-191) =================
-    const float* pf = d_pitchf + (rt ? skip_head : 0);
-    float* phase = ar.alloc<float>((size_t)Td + 8);
-    float* har = ar.alloc<float>((size_t)Td * upp);
-    sine_source(pf, Td, upp, c.sr, d_noise_src, h->lin_w, h->lin_b, phase, har, st);
+    float* har = nullptr;
+    if (h->use_f0) {
+        const float* pf = d_pitchf + (rt ? skip_head : 0);
+        float* phase = ar.alloc<float>((size_t)Td + 8);
+        har = ar.alloc<float>((size_t)Td * upp);
+        sine_source(pf, Td, upp, c.sr, d_noise_src, h->lin_w, h->lin_b, phase, har, st);
+    }
     const float* zdec = z;
     if (Tn != Td) {
-        float* har2 = ar.alloc<float>((size_t)Tn * upp);
-        interp_linear_rows(har, Td * upp, har2, Tn * upp, 1, st);
-        har = har2;
+        if (h->use_f0) {
+            float* har2 = ar.alloc<float>((size_t)Tn * upp);
+            interp_linear_rows(har, Td * upp, har2, Tn * upp, 1, st);
+            har = har2;
+        }
         float* z2 = ar.alloc<float>((size_t)Tn * I);
         interp_linear_rows(z, Td, z2, Tn, I, st);
         zdec = z2;
@@ -507,7 +518,8 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             g.bias = S.up_b; g.out32 = xs32; g.ld32 = (long)S.s * C;
             gemm(g, st);
         }
-        noise_conv_add(xs32, xs16, har, n_har, S.noise_w, S.noise_b, Tout, C, S.noise_k, S.noise_stride, S.noise_pad, 0.1f, st);
+        if (h->use_f0) noise_conv_add(xs32, xs16, har, n_har, S.noise_w, S.noise_b, Tout, C, S.noise_k, S.noise_stride, S.noise_pad, 0.1f, st);
+        else lrelu_cast(xs32, xs16, (long)Tout * C, 0.1f, st);
         const bool last_stage = (i + 1 == c.n_upsamples);
         const int nk = c.n_resblock_kernels;
         for (int j = 0; j < nk; ++j) {
@@ -565,7 +577,8 @@ int rvcb_synth_infer(rvcb_synth* h, const float* d_phone, int T, int sid, const 
                      const float* d_noise_prior, const float* d_noise_src, int skip_head, int return_length, int return_length2,
                      float* d_wav_out, int* n_out, void* stream) {
     RVCB_API_BEGIN
-    RVCB_CHECK(h && d_phone && d_pitch && d_pitchf && d_noise_prior && d_noise_src && d_wav_out, "null argument (f0 models only)");
+    RVCB_CHECK(h && d_phone && d_noise_prior && d_wav_out, "null argument");
+    RVCB_CHECK(!h->use_f0 || (d_pitch && d_pitchf && d_noise_src), "f0 model: pitch, pitchf and the source noise are required");
     synth_forward(h, d_phone, T, sid, (const long long*)d_pitch, d_pitchf, d_noise_prior, d_noise_src, skip_head, return_length,
                   return_length2, d_wav_out, n_out, (cudaStream_t)stream);
     RVCB_API_END

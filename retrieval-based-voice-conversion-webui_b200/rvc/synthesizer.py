@@ -28,8 +28,6 @@ class SynthesizerB200:
         version = cpt.get("version", "v1")
         self.encoder_dim = 256 if version == "v1" else 768
         self.use_f0 = cpt.get("f0", 1) == 1
-        if not self.use_f0:
-            raise NotImplementedError("no-f0 Generator decoder is a 'next' row (SURVEY §8f-4); f0 models only")
         self.config = list(cpt["config"])
         self.device = dev
         self._synth = Synth(_fold_weight_norm(cpt["weight"]), self.config, self.encoder_dim, dev.index or 0)
@@ -58,7 +56,7 @@ class SynthesizerB200:
         T = phone.shape[1]
         if int(phone_lengths.reshape(-1)[0]) != T:
             raise ValueError("phone_lengths must equal the number of phone frames")
-        if pitch is None or pitchf is None:
+        if self.use_f0 and (pitch is None or pitchf is None):
             raise ValueError("f0 model needs pitch and pitchf")
         if skip_head is not None and return_length is not None:
             flow_head = max(int(skip_head) - 24, 0)
@@ -70,11 +68,14 @@ class SynthesizerB200:
             n1, n2 = self._noise.pop(0)
         else:   # synthesizers.py:180,188 randn_like(m_p); generators.py:160,192 rand(1,1,1) + randn_like(sine_waves)
             n1 = torch.randn(1, self.inter, Tf, device=self.device)
-            torch.rand(1, 1, 1, device=self.device)
-            n2 = torch.randn(1, Td * self.upp, 1, device=self.device)
-        out = self._synth.infer(phone[0].to(self.device), int(sid.reshape(-1)[0]), pitch.reshape(-1)[:T].to(self.device),
-                                pitchf.reshape(-1)[:T].to(self.device), n1.to(self.device), n2.to(self.device), skip_head,
-                                return_length, return_length2)
+            n2 = None
+            if self.use_f0:
+                torch.rand(1, 1, 1, device=self.device)
+                n2 = torch.randn(1, Td * self.upp, 1, device=self.device)
+        out = self._synth.infer(phone[0].to(self.device), int(sid.reshape(-1)[0]),
+                                pitch.reshape(-1)[:T].to(self.device) if self.use_f0 else None,
+                                pitchf.reshape(-1)[:T].to(self.device) if self.use_f0 else None, n1.to(self.device),
+                                None if n2 is None else n2.to(self.device), skip_head, return_length, return_length2)
         return out.view(1, 1, -1)
 
 

@@ -239,15 +239,16 @@ class Synth:
             _lib.check(_lib.lib().rvcb_synth_create(C.byref(self.cfg), w.h, C.byref(self.h)))
         self.device = torch.device("cuda", device)
 
-    def infer(self, phone: torch.Tensor, sid: int, pitch: torch.Tensor, pitchf: torch.Tensor, noise_prior: torch.Tensor,
-              noise_src: torch.Tensor, skip_head: Optional[int] = None, return_length: Optional[int] = None,
+    def infer(self, phone: torch.Tensor, sid: int, pitch: Optional[torch.Tensor], pitchf: Optional[torch.Tensor], noise_prior: torch.Tensor,
+              noise_src: Optional[torch.Tensor], skip_head: Optional[int] = None, return_length: Optional[int] = None,
               return_length2: Optional[int] = None) -> torch.Tensor:
+        """pitch / pitchf / noise_src are None for no-f0 models (``cpt["f0"] == 0``)."""
         phone = _chk_dev(phone.reshape(-1, phone.shape[-1]), torch.float32, "phone")
         T = phone.shape[0]
-        pitch = _chk_dev(pitch.reshape(-1), torch.int64, "pitch")
-        pitchf = _chk_dev(pitchf.reshape(-1), torch.float32, "pitchf")
+        pitch = None if pitch is None else _chk_dev(pitch.reshape(-1), torch.int64, "pitch")
+        pitchf = None if pitchf is None else _chk_dev(pitchf.reshape(-1), torch.float32, "pitchf")
         noise_prior = _chk_dev(noise_prior.reshape(self.inter, -1), torch.float32, "noise_prior")
-        noise_src = _chk_dev(noise_src.reshape(-1), torch.float32, "noise_src")
+        noise_src = None if noise_src is None else _chk_dev(noise_src.reshape(-1), torch.float32, "noise_src")
         T_dec = T if return_length is None else int(return_length)
         T_out = T_dec if return_length2 is None else int(return_length2)
         out = torch.empty(T_out * self.upp, device=phone.device, dtype=torch.float32)

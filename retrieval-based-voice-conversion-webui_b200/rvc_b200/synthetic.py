@@ -50,7 +50,7 @@ class _Gen:
 # synthesizer  (SynthesizerTrnMs{256,768}NSFsid, weight-norm removed)
 # --------------------------------------------------------------------------
 def synth_weights(seed: int = 1234, config: List = V2_48K_CONFIG,
-                  encoder_dim: int = 768) -> Dict[str, torch.Tensor]:
+                  encoder_dim: int = 768, use_f0: bool = True) -> Dict[str, torch.Tensor]:
     (spec, seg, inter, hidden, filt, n_heads, n_layers, ksz, _pd, _rb, rb_k, rb_d,
      up_rates, up_init, up_k, n_spk, gin, _sr) = config
     G = _Gen(seed)
@@ -125,6 +125,9 @@ def synth_weights(seed: int = 1234, config: List = V2_48K_CONFIG,
                     w[f"dec.resblocks.{r}.{nm}.{c}.bias"] = G.n((ch,), 0.05)
     w["dec.conv_post.weight"] = G.n((1, ch, 7), 0.35 / math.sqrt(ch * 7))
     w["emb_g.weight"] = G.n((n_spk, gin), 0.5)
+    if not use_f0:      # SynthesizerTrnMs*NSFsid_nono: TextEncoder without emb_pitch, plain Generator decoder (generators.py:14-113)
+        for k in [k for k in w if k.startswith("enc_p.emb_pitch") or k.startswith("dec.m_source") or k.startswith("dec.noise_convs")]:
+            del w[k]
     return w
 
 
@@ -135,13 +138,13 @@ def is_weight_normed(key: str) -> bool:
             or ".enc.cond_layer." in key or ".enc.in_layers." in key or ".enc.res_skip_layers." in key)
 
 
-def synth_cpt(seed: int = 1234, version: str = "v2", config: List = None) -> dict:
+def synth_cpt(seed: int = 1234, version: str = "v2", config: List = None, f0: int = 1) -> dict:
     """A dict shaped like the small inference ``.pth``
     (infer/lib/train/process_ckpt.py:15-54)."""
     if config is None:
         config = V2_48K_CONFIG if version == "v2" else V1_40K_CONFIG
     enc = 768 if version == "v2" else 256
-    wt = synth_weights(seed, config, enc)
+    wt = synth_weights(seed, config, enc, use_f0=(f0 == 1))
     sd = {}
     for k, v in wt.items():
         if k.endswith(".weight") and is_weight_normed(k):
@@ -154,7 +157,7 @@ def synth_cpt(seed: int = 1234, version: str = "v2", config: List = None) -> dic
             sd[k] = v.half()
     return {"weight": sd, "config": list(config),
             "info": "synthetic", "sr": {48000: "48k", 40000: "40k", 32000: "32k"}[config[-1]],
-            "f0": 1, "version": version}
+            "f0": f0, "version": version}
 
 
 # --------------------------------------------------------------------------

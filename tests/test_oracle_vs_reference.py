@@ -38,6 +38,15 @@ torch.manual_seed(6); ref = net_g.infer(phone, torch.tensor([T]), torch.tensor([
 torch.manual_seed(6); n1 = torch.randn(1, 192, T - 16); torch.rand(1, 1, 1); n2 = torch.randn(1, 12 * 480, 1)
 out = OS.synth_infer(w, cpt["config"], phone, torch.tensor([T]), torch.tensor([2]), pitch, pitchf, n1, n2, 40, 12, 14)
 assert out.shape == ref.shape and (out - ref).abs().max().item() < 5e-6
+# no-f0 family (SynthesizerTrnMs768NSFsid_nono: no emb_pitch, plain Generator decoder)
+cpt0 = OW.synth_cpt(5, "v2", f0=0)
+net0, _ = get_synthesizer({**cpt0, "weight": dict(cpt0["weight"]), "config": list(cpt0["config"])}, "cpu")
+w0 = OW.synth_weights(5, use_f0=False)
+assert set(net0.state_dict()) == set(w0)
+torch.manual_seed(3); ref = net0.infer(phone, torch.tensor([T]), torch.tensor([1]))
+torch.manual_seed(3); n1 = torch.randn(1, 192, T)
+out = OS.synth_infer(w0, cpt0["config"], phone, torch.tensor([T]), torch.tensor([1]), None, None, n1, None)
+assert out.shape == ref.shape and (out - ref).abs().max().item() < 5e-6
 m = E2E(4, 1, (2, 2)).eval(); rw = OW.rmvpe_weights(9)
 assert set(m.state_dict()) == set(rw)
 m.load_state_dict(rw)

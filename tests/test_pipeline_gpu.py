@@ -163,3 +163,29 @@ def test_vc_single_with_index_file_and_vc_multi(tmp_path):
     assert outs == ["u0.wav.wav", "u1.wav.wav"]
     sr, y = wavfile.read(str(outdir / outs[0]))
     assert sr == 48000 and len(y) > 40000
+
+
+def test_no_f0_model_through_the_facade_and_realtime_engine():
+    """cpt["f0"] == 0 end to end: get_vc picks the no-f0 container (modules.py:87-99 class table), the pipeline skips
+    RMVPE (pipeline.py:203) and passes pitch=None, rtrvc skips its pitch cache (rtrvc.py:if_f0)."""
+    from infer.lib.rtrvc import RVC
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.5, 1200)
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    cpt = OW.synth_cpt(11, "v2", f0=0)
+    vc.get_vc(cpt)
+    assert vc.if_f0 == 0
+    gidx = Index.from_oracle_layout(idx)
+    info, (sr, wav) = vc.vc_single(0, audio, 0, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+    assert info.startswith("Success"), info
+    assert sr == 48000 and wav.dtype == np.int16 and wav.shape[0] == 71040 and np.abs(wav).max() > 100
+    rt = RVC(0, 0, cpt, gidx, 0.5, device="cuda:0", hubert_model=vc.hubert_model, rmvpe_state_dict=rw)
+    assert rt.if_f0 == 0
+    win = torch.from_numpy(OW.synth_voice(2.72, seed=9).numpy()[:43520]).cuda()
+    y = rt.infer(win, 2560, 250, 21, "rmvpe")
+    assert y.shape == (21 * 480,) and torch.isfinite(y).all()

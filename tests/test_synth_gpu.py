@@ -88,3 +88,24 @@ def test_synth_realtime_formant_shift_resize():
     out = Synth(w, cfg, 768).infer(phone[0].cuda(), 0, pitch[0].cuda(), pitchf[0].cuda(), n1[0].cuda(), n2.reshape(-1).cuda(), skip_head, rl, rl2).cpu()
     assert out.shape == ref.shape == (rl2 * 480,)
     assert (out - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("rt", [False, True])
+def test_synth_no_f0_model_matches_oracle(rt):
+    """SynthesizerTrnMs768NSFsid_nono (rvc/layers/synthesizers.py, use_f0=False): TextEncoder without the pitch
+    embedding and the plain Generator decoder (generators.py:14-113), offline and skip_head variants."""
+    from oracle import synth as OS, weights as OW
+    from rvc_b200.engine import Synth
+    cfg = OW.V2_48K_CONFIG
+    w = OW.synth_weights(77, use_f0=False)
+    assert "enc_p.emb_pitch.weight" not in w and "dec.noise_convs.0.weight" not in w
+    T = 120
+    phone, _, _, g = _inputs(T, seed=3)
+    skip_head, rl = (90, 25) if rt else (None, None)
+    n1 = torch.randn(1, 192, T - (skip_head - 24 if rt else 0), generator=g)
+    with torch.no_grad():
+        ref = OS.synth_infer(w, cfg, phone, torch.tensor([T]), torch.tensor([2]), None, None, n1, None, skip_head, rl, rl)[0, 0]
+    m = Synth(w, cfg, 768)
+    out = m.infer(phone[0].cuda(), 2, None, None, n1[0].cuda(), None, skip_head, rl, rl).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 1e-3
