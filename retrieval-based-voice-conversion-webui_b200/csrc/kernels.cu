@@ -199,18 +199,6 @@ void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s) {
     KERNEL_CHECK();
     count_launch();
 }
-__global__ void lrelu_cast_kernel(const float* __restrict__ x, __half* __restrict__ y, long n, float slope) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const float v = x[i];
-        y[i] = __float2half_rn(v > 0.f ? v : v * slope);
-    }
-}
-void lrelu_cast(const float* x, __half* y, long n, float slope, cudaStream_t s) {
-    lrelu_cast_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(x, y, n, slope);
-    KERNEL_CHECK();
-    count_launch();
-}
 __global__ void half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
     pdl_trigger();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,27 +364,79 @@ void sine_source(const float* f0, int T, int upp, int sr, const float* noise, fl
     count_launch(2);
 }
 
-__global__ void noise_conv_kernel(float* __restrict__ x, __half* __restrict__ x16, const float* __restrict__ har, long n_har,
-                                  const float* __restrict__ w, const float* __restrict__ b, int T, int C, int k, int stride, int pad,
-                                  float slope) {
+// Harmonic-source columns of a vocoder stage input: out[t, m] = (half) har[t * step + m - pad] for m < m_valid and an
+// in-range source index, else 0.  These columns are the A operand of the noise convolution folded into the ups GEMM.
+__global__ void har_columns_kernel(const float* __restrict__ har, long n_har, __half* __restrict__ out, long ld, int T, int Mp, int m_valid,
+                                   int step, int pad) {
     pdl_trigger();
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)T * C) return;
-    const long t = i / C;
-    const int c = (int)(i - t * C);
-    float acc = b[c];
-    const long base = t * stride - pad;
-    for (int j = 0; j < k; ++j) {
-        const long q = base + j;
-        if (q >= 0 && q < n_har) acc = fmaf(har[q], w[j * C + c], acc);      // w is [k, C] (coalesced across channels)
-    }
-    const float y = x[i] + acc;
-    x[i] = y;
-    x16[i] = __float2half_rn(y > 0.f ? y : y * slope);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // T * Mp / 2 < 2^31 (pairs of columns)
+    const int half_m = Mp >> 1;
+    if (i >= T * half_m) return;
+    const int t = i / half_m;
+    const int m = (i - t * half_m) * 2;
+    const long q = (long)t * step + m - pad;
+    const float a = (m < m_valid && q >= 0 && q < n_har) ? har[q] : 0.f;
+    const float b = (m + 1 < m_valid && q + 1 >= 0 && q + 1 < n_har) ? har[q + 1] : 0.f;
+    *reinterpret_cast<__half2*>(out + (long)t * ld + m) = __floats2half2_rn(a, b);
 }
-void noise_conv_add(float* x, __half* x16, const float* har, long n_har, const float* w, const float* b, int T, int C, int k,
-                    int stride, int pad, float slope, cudaStream_t s) {
-    noise_conv_kernel<<<(unsigned)ceil_div_l((long)T * C, 256), 256, 0, s>>>(x, x16, har, n_har, w, b, T, C, k, stride, pad, slope);
+void har_columns(const float* har, long n_har, __half* out, long ld, int T, int Mp, int m_valid, int step, int pad, cudaStream_t s) {
+    RVCB_CHECK(Mp % 2 == 0 && ld % 2 == 0 && (long)T * (Mp / 2) < (1L << 31), "har_columns: bad shape");
+    har_columns_kernel<<<(unsigned)ceil_div_l((long)T * (Mp / 2), 256), 256, 0, s>>>(har, n_har, out, ld, T, Mp, m_valid, step, pad);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// conv_post (Conv1d(C, 1, k, padding k/2, bias=False) + tanh, nsf.py:187-189): one output channel is a bandwidth-bound
+// reduction, not a GEMM.  A block stages (256 + k - 1) input rows in shared memory (row stride C*2 + 16 B: conflict-free
+// 16-byte reads at one row per thread) and each thread reduces its k x C window in fp32.
+template <int C>
+__global__ void __launch_bounds__(256) conv_post_kernel(const __half* __restrict__ x, int T, const float* __restrict__ w /*[k, C]*/, int k,
+                                                        float* __restrict__ out) {
+    pdl_trigger();
+    constexpr int RS = C * 2 + 16;               // bytes per staged row
+    constexpr int V = C / 8;                     // uint4 per row
+    extern __shared__ __align__(16) unsigned char smem_cp[];
+    float* sw = reinterpret_cast<float*>(smem_cp);
+    unsigned char* sx = smem_cp + ((k * C * 4 + 15) & ~15);
+    const int pad = k / 2;
+    const int t0 = blockIdx.x * 256;
+    const int rows = 256 + k - 1;
+    for (int i = threadIdx.x; i < k * C; i += 256) sw[i] = w[i];
+    for (int i = threadIdx.x; i < rows * V; i += 256) {
+        const int r = i / V, v = i - r * V;
+        const int t = t0 + r - pad;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && t < T) val = *reinterpret_cast<const uint4*>(x + (long)t * C + v * 8);
+        *reinterpret_cast<uint4*>(sx + r * RS + v * 16) = val;
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= T) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < k; ++j) {
+        const unsigned char* row = sx + (threadIdx.x + j) * RS;
+        const float* wj = sw + j * C;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint4 q = *reinterpret_cast<const uint4*>(row + v * 16);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                acc[e] = fmaf(f.x, wj[v * 8 + 2 * e], acc[e]);
+                acc[e] = fmaf(f.y, wj[v * 8 + 2 * e + 1], acc[e]);
+            }
+        }
+    }
+    out[t] = tanhf((acc[0] + acc[1]) + (acc[2] + acc[3]));
+}
+void conv_post_tanh(const __half* x, int T, int C, const float* w, int k, float* out, cudaStream_t s) {
+    RVCB_CHECK((C == 32 || C == 16 || C == 64) && k >= 1 && k <= 15, "conv_post: unsupported shape");
+    const size_t smem = ((size_t)k * C * 4 + 15) / 16 * 16 + (size_t)(256 + k - 1) * (C * 2 + 16);
+    const unsigned grid = (unsigned)ceil_div_l(T, 256);
+    if (C == 32) conv_post_kernel<32><<<grid, 256, smem, s>>>(x, T, w, k, out);
+    else if (C == 16) conv_post_kernel<16><<<grid, 256, smem, s>>>(x, T, w, k, out);
+    else conv_post_kernel<64><<<grid, 256, smem, s>>>(x, T, w, k, out);
     KERNEL_CHECK();
     count_launch();
 }

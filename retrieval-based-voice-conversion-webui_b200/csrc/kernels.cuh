@@ -19,7 +19,6 @@ void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, c
 
 void cast_f32_f16(const float* x, __half* y, long n, cudaStream_t s);
 void half_to_float(const __half* x, float* y, long n, cudaStream_t s);   // exact widening
-void lrelu_cast(const float* x, __half* y, long n, float slope, cudaStream_t s);   // y = (half) leaky_relu(x)
 // y[r, c] = x[r, c] for a [rows, cols] fp32 matrix with leading dims -> fp16
 void cast_f32_f16_2d(const float* x, long ldx, __half* y, long ldy, int rows, int cols, cudaStream_t s);
 
@@ -39,9 +38,11 @@ void add_rowvec(float* x, const float* v, int T, int C, __half* out16, float lre
 // NSF source (generators.py:148-194 + nsf.py:57-61): f0 [T] -> har fp32 [T*upp]
 void sine_source(const float* f0, int T, int upp, int sr, const float* noise, float lin_w, float lin_b, float* phase_scratch,
                  float* har, cudaStream_t s);
-// x[t, c] += sum_j har[t*stride + j - pad] * w[j, c] + b[c];  x16 = lrelu(x, slope)   (w transposed to [k, C])
-void noise_conv_add(float* x, __half* x16, const float* har, long n_har, const float* w, const float* b, int T, int C, int k,
-                    int stride, int pad, float slope, cudaStream_t s);
+// out[t, m] = (half) har[t*step + m - pad]  (0 for m >= m_valid or outside the source): the harmonic-source columns appended
+// to a vocoder stage input, so the noise convolution rides in the ups GEMM as one more K segment
+void har_columns(const float* har, long n_har, __half* out, long ld, int T, int Mp, int m_valid, int step, int pad, cudaStream_t s);
+// out[t] = tanh(sum_{j,c} x[t + j - k/2, c] * w[j, c])   (conv_post, one output channel; x fp16 [T, C] dense)
+void conv_post_tanh(const __half* x, int T, int C, const float* w, int k, float* out, cudaStream_t s);
 // linear interpolation along time (F.interpolate mode="linear", align_corners=False) of [T_in, C] -> [T_out, C]
 void interp_linear_rows(const float* in, int T_in, float* out, int T_out, int C, cudaStream_t s);
 

@@ -31,7 +31,8 @@ struct ResBlock {
 };
 struct Stage {
     PackedB up; float* up_b; int s, k, cin, cout;
-    float *noise_w, *noise_b; int noise_k, noise_stride, noise_pad;
+    int noise_k, noise_stride, noise_pad;   // noise conv (nsf.py:176-183), folded into the ups GEMM as extra K columns
+    int Mp;                                 // padded count of harmonic-source columns appended to the ups GEMM's A rows (0: no-f0)
     ResBlock rb[4];
 };
 
@@ -64,7 +65,7 @@ struct rvcb_synth {
     // dec
     PackedB conv_pre; float *conv_pre_b = nullptr, *dcond_w = nullptr, *dcond_b = nullptr;
     std::vector<Stage> stages;
-    PackedB conv_post;
+    float* conv_post_w = nullptr; int conv_post_k = 0;   // [k, C] fp32
     float lin_w = 1.f, lin_b = 0.f;
 };
 
@@ -202,31 +203,33 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
             RVCB_CHECK(S.k <= 2 * S.s + (S.k - S.s) % 2 && S.k >= S.s, "synth: upsample kernel must satisfy s <= k <= 2s");
             const std::string us = "dec.ups." + std::to_string(i);
             const std::vector<float> uw = effective_weight(w, us);
-            S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, 64);
             std::vector<float> ub((size_t)S.s * S.cout);
             const WT& ubias = w.get(us + ".bias");
-            for (int r = 0; r < S.s; ++r)
-                for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co];
-            S.up_b = own.upload(ub);
+            RVCB_CHECK(S.cin % 64 == 0, "synth: upsample input channels must be multiples of 64");
             if (h->use_f0) {
-            const WT& nw = w.get("dec.noise_convs." + std::to_string(i) + ".weight");
-            S.noise_k = (int)nw.dim(2);
-            if (i + 1 < c.n_upsamples) {
-                int st = 1;
-                for (int j = i + 1; j < c.n_upsamples; ++j) st *= c.upsample_rates[j];
-                S.noise_stride = st; S.noise_pad = st / 2;
-                RVCB_CHECK(S.noise_k == 2 * st, "synth: noise conv kernel mismatch");
+                const WT& nw = w.get("dec.noise_convs." + std::to_string(i) + ".weight");
+                const WT& nb = w.get("dec.noise_convs." + std::to_string(i) + ".bias");
+                S.noise_k = (int)nw.dim(2);
+                if (i + 1 < c.n_upsamples) {
+                    int st = 1;
+                    for (int j = i + 1; j < c.n_upsamples; ++j) st *= c.upsample_rates[j];
+                    S.noise_stride = st; S.noise_pad = st / 2;
+                    RVCB_CHECK(S.noise_k == 2 * st, "synth: noise conv kernel mismatch");
+                } else {
+                    S.noise_stride = 1; S.noise_pad = 0;
+                }
+                S.Mp = round_up((S.s - 1) * S.noise_stride + S.noise_k, 64);
+                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, 64, nw.data.data(), S.noise_k,
+                                    S.noise_stride, S.Mp);
+                for (int r = 0; r < S.s; ++r)
+                    for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co] + nb.data[co];
             } else {
-                S.noise_stride = 1; S.noise_pad = 0;
+                S.Mp = 0;
+                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, 64);
+                for (int r = 0; r < S.s; ++r)
+                    for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co];
             }
-            {   // [C, 1, k] -> [k, C]
-                std::vector<float> nt((size_t)S.noise_k * S.cout);
-                for (int co = 0; co < S.cout; ++co)
-                    for (int j = 0; j < S.noise_k; ++j) nt[(size_t)j * S.cout + co] = nw.data[(size_t)co * S.noise_k + j];
-                S.noise_w = own.upload(nt);
-            }
-            S.noise_b = own.upload(w.get("dec.noise_convs." + std::to_string(i) + ".bias").data);
-            }
+            S.up_b = own.upload(ub);
             ch = S.cout;
             const int bk = ch >= 64 ? 64 : 32;
             RVCB_CHECK(ch % 32 == 0, "synth: decoder channels must be multiples of 32");
@@ -246,7 +249,15 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
             }
             h->stages.push_back(S);
         }
-        h->conv_post = pack_conv1d(own, w.get("dec.conv_post.weight").data.data(), 1, ch, 7, ch >= 64 ? 64 : 32);
+        {   // [1, C, k] -> [k, C]
+            const WT& pw = w.get("dec.conv_post.weight");
+            const int kp = (int)pw.dim(2);
+            std::vector<float> t((size_t)kp * ch);
+            for (int ci = 0; ci < ch; ++ci)
+                for (int j = 0; j < kp; ++j) t[(size_t)j * ch + ci] = pw.data[(size_t)ci * kp + j];
+            h->conv_post_w = own.upload(t);
+            h->conv_post_k = kp;
+        }
     } catch (...) {
         delete h;
         throw;
@@ -276,17 +287,20 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     need += rnd((size_t)T * 2 * heads * HP * 2) + rnd((size_t)H * Tp * 2) + rnd((size_t)heads * T * Tp * 4) + rnd((size_t)heads * T * Tp * 2);
     need += rnd((size_t)heads * T * 32 * 4) + rnd((size_t)heads * T * 64 * 2) + rnd((size_t)T * F * 2) + rnd((size_t)T * 2 * I * 4);
     need += 6 * rnd((size_t)Tf * H * 4) + 4 * rnd((size_t)Tf * H * 2);
-    need += 2 * rnd((size_t)Tn * upp * 4) + rnd((size_t)Tn * c.upsample_initial_channel * 2) + 2 * rnd((size_t)Tn * I * 4);
+    need += 2 * rnd((size_t)Tn * upp * 4) + rnd((size_t)Tn * (c.upsample_initial_channel + h->stages[0].Mp) * 2) + 2 * rnd((size_t)Tn * I * 4);
+    size_t carry_e = 0;      // halves per carry buffer: widest [T_in, C_in + Mp] input of stages 1.. and the last stage's output
     {
         size_t mx = 0;
         int Tt = Tn, ch = c.upsample_initial_channel;
         for (int i = 0; i < c.n_upsamples; ++i) {
+            if (i > 0) carry_e = std::max(carry_e, (size_t)Tt * (ch + h->stages[i].Mp));
             Tt *= c.upsample_rates[i];
             ch /= 2;
             const size_t e = (size_t)Tt * ch;
-            mx = std::max(mx, 3 * rnd(e * 4) + 6 * rnd(e * 2));
+            mx = std::max(mx, 3 * rnd(e * 4) + 4 * rnd(e * 2));
         }
-        need += mx + rnd((size_t)Tn * upp * 32 * 2);
+        carry_e = std::max(carry_e, (size_t)Tt * ch);
+        need += mx + 2 * rnd(carry_e * 2);
     }
     h->arena.reserve(need);
     h->arena.reset();
@@ -477,24 +491,16 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     const int C0 = c.upsample_initial_channel;
     float* pre_b = ar.alloc<float>(C0);
     matvec(h->dcond_w, gvec, h->dcond_b, h->conv_pre_b, pre_b, C0, c.gin_channels, st);
-    __half* xin16 = ar.alloc<__half>((size_t)Tn * C0);
+    const long ld_in0 = C0 + h->stages[0].Mp;       // stage inputs are [T_in, C_in | Mp harmonic-source columns]
+    __half* xin16 = ar.alloc<__half>((size_t)Tn * ld_in0);
     {
         GemmArgs g = mk(z16, I, Tn, I, h->conv_pre, Tn, C0);
         seg_conv1d(g, I, 7, 1, 3);
-        g.bias = pre_b; g.act2 = ACT_LRELU; g.act2_p = 0.1f; g.out16 = xin16; g.ld16 = C0;
+        g.bias = pre_b; g.act2 = ACT_LRELU; g.act2_p = 0.1f; g.out16 = xin16; g.ld16 = ld_in0;
         gemm(g, st);
     }
     int Tt = Tn;
-    size_t max_e = 0;
-    {
-        int t2 = Tn, ch2 = C0;
-        for (int i = 0; i < c.n_upsamples; ++i) {
-            t2 *= c.upsample_rates[i];
-            ch2 /= 2;
-            max_e = std::max(max_e, (size_t)t2 * ch2);
-        }
-    }
-    __half* carry[2] = {ar.alloc<__half>(max_e), ar.alloc<__half>(max_e)};   // lrelu(x) handed from stage to stage
+    __half* carry[2] = {ar.alloc<__half>(carry_e), ar.alloc<__half>(carry_e)};   // lrelu(x) handed from stage to stage
     const size_t stage_mark = ar.off;
     __half* carry16 = nullptr;
     for (int i = 0; i < c.n_upsamples; ++i) {
@@ -511,16 +517,22 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
         __half* xs16 = ar.alloc<__half>(e);
         __half* y16 = ar.alloc<__half>(e);
         __half* t16 = ar.alloc<__half>(e);
-        {   // ConvTranspose1d as a polyphase GEMM: [Tin, s*C] == [Tout, C]
-            GemmArgs g = mk(prev16, S.cin, Tin, S.cin, S.up, Tin, S.s * C);
+        const long ld_in = S.cin + S.Mp;
+        const bool last_stage = (i + 1 == c.n_upsamples);
+        const long ld_next = last_stage ? C : (C + h->stages[i + 1].Mp);
+        if (S.Mp)   // column m of row t_in: har[t_in * s * stride_n + m - pad] (zero outside the source / past the taps)
+            har_columns(har, n_har, prev16 + S.cin, ld_in, Tin, S.Mp, (S.s - 1) * S.noise_stride + S.noise_k, S.s * S.noise_stride,
+                        S.noise_pad, st);
+        {   // ConvTranspose1d as a polyphase GEMM: [Tin, s*C] == [Tout, C]; + the noise conv as one more K segment.
+            // Epilogue emits x (fp32 residual stream) and lrelu(x) (fp16 operand of the first resblock convs).
+            GemmArgs g = mk(prev16, ld_in, Tin, (int)ld_in, S.up, Tin, S.s * C);
             g.nseg = 3;
-            for (int d = 0; d < 3; ++d) g.seg[d] = {d - 1, 0, 0, ceil_div(S.cin, 64)};
+            for (int d = 0; d < 3; ++d) g.seg[d] = {d - 1, 0, 0, S.cin / 64};
+            if (S.Mp) g.seg[g.nseg++] = {0, S.cin, 0, S.Mp / 64};
             g.bias = S.up_b; g.out32 = xs32; g.ld32 = (long)S.s * C;
+            g.out16 = xs16; g.ld16 = (long)S.s * C; g.act2 = ACT_LRELU; g.act2_p = 0.1f;
             gemm(g, st);
         }
-        if (h->use_f0) noise_conv_add(xs32, xs16, har, n_har, S.noise_w, S.noise_b, Tout, C, S.noise_k, S.noise_stride, S.noise_pad, 0.1f, st);
-        else lrelu_cast(xs32, xs16, (long)Tout * C, 0.1f, st);
-        const bool last_stage = (i + 1 == c.n_upsamples);
         const int nk = c.n_resblock_kernels;
         for (int j = 0; j < nk; ++j) {
             const ResBlock& R = S.rb[j];
@@ -543,7 +555,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
                         if (j > 0) { g.res2 = sum32; g.ldres2 = C; }
                         g.out32 = sum32; g.ld32 = C;
                         if (j == nk - 1) {
-                            g.out16 = next16; g.ld16 = C; g.act2 = ACT_LRELU; g.act2_p = last_stage ? 0.01f : 0.1f;
+                            g.out16 = next16; g.ld16 = ld_next; g.act2 = ACT_LRELU; g.act2_p = last_stage ? 0.01f : 0.1f;
                         }
                     }
                     gemm(g, st);
@@ -553,14 +565,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
         carry16 = next16;
         Tt = Tout;
     }
-    {
-        const int C = h->stages.back().cout;
-        const int bk = C >= 64 ? 64 : 32;
-        GemmArgs g = mk(carry16, C, Tt, C, h->conv_post, Tt, 1, bk);
-        seg_conv1d(g, C, 7, 1, 3);
-        g.act1 = ACT_TANH; g.out32 = d_wav_out; g.ld32 = 1;
-        gemm(g, st);
-    }
+    conv_post_tanh(carry16, Tt, h->stages.back().cout, h->conv_post_w, h->conv_post_k, d_wav_out, st);
     if (n_out) *n_out = Tt;
 }
 

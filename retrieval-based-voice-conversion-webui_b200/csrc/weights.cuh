@@ -92,18 +92,29 @@ inline PackedB pack_conv1d(DevOwner& own, const float* W, int Cout, int Cin, int
 
 // ConvTranspose1d weight [Cin, Cout, k], stride s, padding p -> polyphase [s*Cout, 3*Cin_pad]
 // row = r*Cout + co; segment index di <-> delta = di-1; tap j = r + p - delta*s
-inline PackedB pack_convT1d(DevOwner& own, const float* W, int Cin, int Cout, int k, int s, int p, int bk = 64) {
+// Optional extra K columns (Mp of them) fold the NSF noise convolution (Conv1d(1, Cout, kn, stride_n) over the harmonic
+// source, nsf.py:176-183) into the same GEMM: the A operand carries har[tin*s*stride_n + m - pad] in column m, and the
+// weight of output phase r at column m is Wn[co, m - r*stride_n].
+inline PackedB pack_convT1d(DevOwner& own, const float* W, int Cin, int Cout, int k, int s, int p, int bk = 64,
+                            const float* Wn = nullptr, int kn = 0, int stride_n = 0, int Mp = 0) {
     const int Cp = pad_to(Cin, bk), Np = pad_to(s * Cout, 16);
-    std::vector<float> h((size_t)Np * 3 * Cp, 0.f);
-    for (int r = 0; r < s; ++r)
+    const int Kt = 3 * Cp + Mp;
+    std::vector<float> h((size_t)Np * Kt, 0.f);
+    for (int r = 0; r < s; ++r) {
         for (int di = 0; di < 3; ++di) {
             const int j = r + p - (di - 1) * s;
             if (j < 0 || j >= k) continue;
             for (int co = 0; co < Cout; ++co)
                 for (int ci = 0; ci < Cin; ++ci)
-                    h[((size_t)(r * Cout + co) * 3 + di) * Cp + ci] = W[((size_t)ci * Cout + co) * k + j];
+                    h[(size_t)(r * Cout + co) * Kt + di * Cp + ci] = W[((size_t)ci * Cout + co) * k + j];
         }
-    return upload_half(own, h, Np, 3 * Cp);
+        for (int m = 0; m < Mp && Wn; ++m) {
+            const int j = m - r * stride_n;
+            if (j < 0 || j >= kn) continue;
+            for (int co = 0; co < Cout; ++co) h[(size_t)(r * Cout + co) * Kt + 3 * Cp + m] = Wn[(size_t)co * kn + j];
+        }
+    }
+    return upload_half(own, h, Np, Kt);
 }
 
 // Conv2d 3x3 weight [Cout, Cin, 3, 3] (+ folded per-output scale) -> [Cout_pad, 9*Cin_pad], (dh, dw, ci) order
