@@ -73,20 +73,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int tiles_per_z = p.num_m_tiles * p.num_n_tiles;
 
     if (warp == 0) {
-        // ======================= TMA producer =======================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int z = tile / tiles_per_z;
-                const int rem = tile - z * tiles_per_z;
-                const int mt = rem / p.num_n_tiles;
-                const int nt = rem - mt * p.num_n_tiles;
-                int kb = 0;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const SegPacked sg = p.seg[s];
-                    for (int kc = 0; kc < sg.nk; ++kc, ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ======================= TMA producer (warp-uniform loop; one elected lane issues) =======================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int z = tile / tiles_per_z;
+            const int rem = tile - z * tiles_per_z;
+            const int mt = rem / p.num_n_tiles;
+            const int nt = rem - mt * p.num_n_tiles;
+            int kb = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const SegPacked sg = p.seg[s];
+                for (int kc = 0; kc < sg.nk; ++kc, ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
                         const int ac0 = z * p.a_col_z + sg.col + kc * BK;
                         if (p.conv2d_W == 0) {
@@ -98,40 +98,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                         tma_load_2d(smem_b + stage * C::B_STAGE, &tmap_b, &full_bar[stage],
                                     p.b_col0 + z * p.b_col_z + kb * BK, nt * BN + z * p.b_row_z);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ======================= MMA issuer (warp-uniform loop; one elected lane issues) =======================
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // smem descriptor = {lo: start address >> 4 | LBO(1) << 16, hi: SBO | version | layout}; a K step of 16 fp16 is +2 in lo
+        constexpr uint32_t desc_hi = (uint32_t)(((uint64_t)((8 * BK * 2) >> 4) << 32 | (1ull << 46) |
+                                                 ((BK == 64 ? 2ull : BK == 32 ? 4ull : 6ull) << 61)) >> 32);
+        const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_c = tmem_base + acc * BN;
+            for (int kb = 0; kb < p.total_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_c = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.total_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * C::A_STAGE);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * C::B_STAGE);
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (uint32_t)(C::A_STAGE / 16);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (uint32_t)(C::B_STAGE / 16);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = make_kmajor_desc<BK>(a_addr + k * 32);
-                        const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
+                        const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                        const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
                         umma_f16(tmem_c, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs retire
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);           // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ======================= epilogue (8 warps) =======================

@@ -19,6 +19,7 @@ namespace rvcb {
 struct WSParams {
     KParams k;              // epilogue / shape fields reused (seg[] holds the taps)
     int rmin, HRp, nkc, n_slices, m_tiles, bo_mode;
+    int has_r2, do16;       // ws2 only: second residual tile / fp16 output present
 };
 
 template <int BN, int BK>
@@ -98,52 +99,59 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int mt_step = gridDim.x / wp.n_slices;
 
     if (warp == 0) {
-        // ======================= TMA producer =======================
-        if (lane == 0) {
+        // ======================= TMA producer (warp-uniform loop, one elected lane issues) =======================
+        if (elect_one()) {
             mbar_expect_tx(b_full, (uint32_t)b_bytes);
             for (int kb = 0; kb < total_kb; ++kb)
                 tma_load_2d(smem_b + kb * C::B_KB_BYTES, &tmap_b, b_full, kb * BK, slice * BN);
-            int it = 0;
-            for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        }
+        __syncwarp();
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&a_full[buf], (uint32_t)(wp.nkc * a_chunk));
                 for (int kc = 0; kc < wp.nkc; ++kc)
                     tma_load_3d(smem_a + buf * a_buf + kc * a_chunk, &tmap_a, &a_full[buf], kc * BK, mt * BM + wp.rmin, 0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            mbar_wait(b_full, 0);
-            int it = 0;
-            for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
-                const int buf = it & 1, acc = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], ph ^ 1);
-                mbar_wait(&a_full[buf], ph);
-                tc_fence_after();
-                const uint32_t tmem_c = tmem_base + acc * BN;
-                const uint32_t a_base = smem_u32(smem_a + buf * a_buf);
-                const uint32_t b_base = smem_u32(smem_b);
-                uint32_t first = 0;
-                for (int kc = 0; kc < wp.nkc; ++kc) {
-                    for (int j = 0; j < p.nseg; ++j) {
-                        const uint32_t a_addr = a_base + kc * a_chunk + (uint32_t)(p.seg[j].row - wp.rmin) * (BK * 2);
-                        const uint32_t b_addr = b_base + (uint32_t)(j * wp.nkc + kc) * C::B_KB_BYTES;
+        // ======================= MMA issuer (warp-uniform loop, one elected lane issues) =======================
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        mbar_wait(b_full, 0);
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            const int buf = it & 1, acc = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], ph ^ 1);
+            mbar_wait(&a_full[buf], ph);
+            tc_fence_after();
+            const uint32_t tmem_c = tmem_base + acc * BN;
+            const uint32_t a_base = smem_u32(smem_a + buf * a_buf);
+            const uint32_t b_base = smem_u32(smem_b);
+            uint32_t first = 0;
+            for (int kc = 0; kc < wp.nkc; ++kc) {
+                for (int j = 0; j < p.nseg; ++j) {
+                    const uint32_t a_addr = a_base + kc * a_chunk + (uint32_t)(p.seg[j].row - wp.rmin) * (BK * 2);
+                    const uint32_t b_addr = b_base + (uint32_t)(j * wp.nkc + kc) * C::B_KB_BYTES;
+                    if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t da = make_desc_shifted<BK>(a_addr + k * 32, wp.bo_mode);
                             const uint64_t db = make_kmajor_desc<BK>(b_addr + k * 32);
-                            umma_f16(tmem_c, da, db, idesc, first);
-                            first = 1;
+                            umma_f16(tmem_c, da, db, idesc, first | (uint32_t)k);
                         }
                     }
+                    first = 1;
                 }
+            }
+            if (elect_one()) {
                 umma_commit(&a_empty[buf]);       // halo buffer free once these MMAs retire
                 umma_commit(&tfull_bar[acc]);     // accumulator complete
             }
+            __syncwarp();
         }
     } else {
         // ======================= epilogue (8 warps, two groups) =======================
@@ -368,6 +376,291 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// v2: same weight-stationary / halo-streaming main loop, but every byte of the epilogue's global traffic moves by TMA.
+//   * the producer prefetches the fp32 residual tile(s) of tile i+1 into swizzled shared memory while tile i computes;
+//   * the 8 epilogue warps go TMEM -> registers -> (+bias, +residual from smem) -> write y (fp32, in place over the residual
+//     tile) and lrelu(y) (fp16) back to shared memory -- no global loads or stores, no exposed HBM latency;
+//   * one elected thread issues the tile stores (cp.async.bulk.tensor, clipped at M) and frees the staging stage.
+// Staging tiles use the TMA 128 B / 64 B swizzle, so "thread = row" 16-byte accesses are bank-conflict free.
+// EPI as above (0: c1, 1: c2, 2: last c2 of a resblock); the generic contract stays on the v1 kernel.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct WS2Cfg {
+    static constexpr int W = BN / 2;                       // columns per epilogue warp (4 lane quadrants x 2 column halves)
+    static constexpr int NPAN = BN / 32;                   // fp32 panels of 32 columns (128-byte rows, SW128)
+    static constexpr int R_BYTES = BM * BN * 4;
+    static constexpr int H_BYTES = BM * BN * 2;            // fp16 tile: BN = 64 -> 128-byte rows (SW128), BN = 32 -> 64-byte rows (SW64)
+    static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : 128;
+    static constexpr int NS = 2;                           // staging stages
+};
+
+template <int BN, int BK, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
+                const __grid_constant__ CUtensorMap tmap_o32, const __grid_constant__ CUtensorMap tmap_o16,
+                const __grid_constant__ WSParams wp) {
+    using C = WS2Cfg<BN>;
+    constexpr int B_KB_BYTES = BN * BK * 2;
+    const KParams& p = wp.k;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int total_kb = p.nseg * wp.nkc;
+    const int b_bytes = total_kb * B_KB_BYTES;
+    const int a_chunk = wp.HRp * BK * 2;
+    const int a_buf = ((wp.nkc * a_chunk + 1023) / 1024) * 1024;
+    const bool has_r2 = (EPI == 2) && wp.has_r2;
+    const bool do16 = (EPI < 2) || wp.do16;
+    uint8_t* smem_b = smem;
+    uint8_t* smem_a = smem + ((b_bytes + 1023) / 1024) * 1024;
+    uint8_t* smem_r1 = smem_a + 2 * a_buf;
+    uint8_t* smem_r2 = smem_r1 + (EPI >= 1 ? C::NS * C::R_BYTES : 0);
+    uint8_t* smem_h = smem_r2 + (has_r2 ? C::NS * C::R_BYTES : 0);
+    uint8_t* tail = smem_h + (do16 ? C::NS * C::H_BYTES : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* b_full = bars;            // [1]
+    uint64_t* a_full = bars + 1;        // [2]
+    uint64_t* a_empty = bars + 3;       // [2]
+    uint64_t* tfull_bar = bars + 5;     // [2]
+    uint64_t* tempty_bar = bars + 7;    // [2]
+    uint64_t* r_full = bars + 9;        // [2] residual tile(s) landed
+    uint64_t* r_empty = bars + 11;      // [2] staging stage drained by the TMA stores
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        if (EPI >= 1) { prefetch_tmap(&tmap_r1); prefetch_tmap(&tmap_o32); }
+        if (has_r2) prefetch_tmap(&tmap_r2);
+        if (do16) prefetch_tmap(&tmap_o16);
+        mbar_init(b_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], kEpiWarps);
+            mbar_init(&r_full[i], 1);
+            mbar_init(&r_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    const int slice = blockIdx.x % wp.n_slices;
+    const int mt0 = blockIdx.x / wp.n_slices;
+    const int mt_step = gridDim.x / wp.n_slices;
+
+    if (warp == 0) {
+        // ======================= TMA producer (warp-uniform loop, one elected lane issues) =======================
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)b_bytes);
+            for (int kb = 0; kb < total_kb; ++kb)
+                tma_load_2d(smem_b + kb * B_KB_BYTES, &tmap_b, b_full, kb * BK, slice * BN);
+        }
+        __syncwarp();
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(&a_empty[buf], ph ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&a_full[buf], (uint32_t)(wp.nkc * a_chunk));
+                for (int kc = 0; kc < wp.nkc; ++kc)
+                    tma_load_3d(smem_a + buf * a_buf + kc * a_chunk, &tmap_a, &a_full[buf], kc * BK, mt * BM + wp.rmin, 0);
+            }
+            __syncwarp();
+            if (EPI >= 1) {
+                mbar_wait(&r_empty[buf], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&r_full[buf], (uint32_t)(C::R_BYTES * (has_r2 ? 2 : 1)));
+#pragma unroll
+                    for (int pn = 0; pn < C::NPAN; ++pn) {
+                        tma_load_2d(smem_r1 + buf * C::R_BYTES + pn * (BM * 128), &tmap_r1, &r_full[buf], slice * BN + pn * 32, mt * BM);
+                        if (has_r2)
+                            tma_load_2d(smem_r2 + buf * C::R_BYTES + pn * (BM * 128), &tmap_r2, &r_full[buf], slice * BN + pn * 32, mt * BM);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer (warp-uniform loop, one elected lane issues) =======================
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // descriptor = {lo: start address >> 4 | LBO(1) << 16, hi: SBO | version | layout}; K step = +32 B = +2 in lo
+        constexpr uint32_t desc_hi = (uint32_t)(((uint64_t)((8 * BK * 2) >> 4) << 32 | (1ull << 46) |
+                                                 ((BK == 64 ? 2ull : BK == 32 ? 4ull : 6ull) << 61)) >> 32);
+        mbar_wait(b_full, 0);
+        const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            const int buf = it & 1, acc = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], ph ^ 1);
+            mbar_wait(&a_full[buf], ph);
+            tc_fence_after();
+            const uint32_t tmem_c = tmem_base + acc * BN;
+            uint32_t first = 0;
+            for (int kc = 0; kc < wp.nkc; ++kc) {
+                const uint32_t a_kc = a_lo0 + (uint32_t)((buf * a_buf + kc * a_chunk) >> 4);
+                for (int j = 0; j < p.nseg; ++j) {
+                    const uint32_t a_lo = a_kc + (uint32_t)(p.seg[j].row - wp.rmin) * (uint32_t)(BK * 2 / 16);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)(j * wp.nkc + kc) * (uint32_t)(B_KB_BYTES / 16);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                            umma_f16(tmem_c, da, db, idesc, first | (uint32_t)k);
+                        }
+                    }
+                    first = 1;
+                }
+            }
+            if (elect_one()) {
+                umma_commit(&a_empty[buf]);
+                umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ======================= epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves =======================
+        constexpr int W = C::W;
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int chalf = ew >> 2;
+        const int r = quarter * 32 + lane;                 // tile row owned by this thread
+        const int c0 = chalf * W;                          // first tile column owned by this thread
+        // swizzled 16-byte chunk addressing (see header comment)
+        const uint32_t r_off = (uint32_t)((c0 >> 5) * (BM * 128) + r * 128);
+        const int r_cb = (c0 & 31) >> 2;
+        const uint32_t h_off = (uint32_t)(r * (BN * 2));
+        const int h_cb = c0 >> 3;
+        const int h_x = (BN == 64) ? (r & 7) : ((r >> 1) & 3);
+        float bias_r[W];
+#pragma unroll
+        for (int i = 0; i < W; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + slice * BN + c0 + i));
+            bias_r[i] = b.x; bias_r[i + 1] = b.y; bias_r[i + 2] = b.z; bias_r[i + 3] = b.w;
+        }
+        const float slope = p.act2_p, alpha = p.alpha;
+        const bool elected = (warp == 2 && lane == 0);
+        int it = 0;
+        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            if (EPI >= 1) mbar_wait(&r_full[s], ph);       // residual landed (the producer waited for the stage to drain)
+            else mbar_wait(&r_empty[s], ph ^ 1);           // staging stage drained
+            mbar_wait(&tfull_bar[s], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + s * BN + c0 + ((uint32_t)(quarter * 32) << 16);
+            float v[W];
+            {
+                uint32_t raw[16];
+                tmem_ld16(taddr, raw);
+                if constexpr (W == 32) {
+                    uint32_t raw2[16];
+                    tmem_ld16(taddr + 16, raw2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[16 + i] = __uint_as_float(raw2[i]);
+                } else {
+                    tmem_ld_wait();
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[s]);    // accumulator stage free as soon as it is in registers
+            uint8_t* R1 = smem_r1 + s * C::R_BYTES + r_off;
+            uint8_t* R2 = smem_r2 + s * C::R_BYTES + r_off;
+            uint8_t* Hs = smem_h + s * C::H_BYTES + h_off;
+#pragma unroll
+            for (int i = 0; i < W / 4; ++i) {
+                float4 t = make_float4(v[4 * i] + bias_r[4 * i], v[4 * i + 1] + bias_r[4 * i + 1], v[4 * i + 2] + bias_r[4 * i + 2],
+                                       v[4 * i + 3] + bias_r[4 * i + 3]);
+                if (EPI >= 1) {
+                    float4* q = reinterpret_cast<float4*>(R1 + (((r_cb + i) ^ (r & 7)) << 4));
+                    const float4 a = *q;
+                    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+                    if (EPI == 2) {
+                        t.x *= alpha; t.y *= alpha; t.z *= alpha; t.w *= alpha;
+                        if (has_r2) {
+                            const float4 b = *reinterpret_cast<const float4*>(R2 + (((r_cb + i) ^ (r & 7)) << 4));
+                            t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+                        }
+                    }
+                    *q = t;                                 // y, in place: this tile is stored to out32
+                }
+                v[4 * i] = t.x > 0.f ? t.x : t.x * slope; v[4 * i + 1] = t.y > 0.f ? t.y : t.y * slope;
+                v[4 * i + 2] = t.z > 0.f ? t.z : t.z * slope; v[4 * i + 3] = t.w > 0.f ? t.w : t.w * slope;
+            }
+            if (do16) {
+#pragma unroll
+                for (int i = 0; i < W / 8; ++i) {
+                    const __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+                    const __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+                    *reinterpret_cast<uint4*>(Hs + (((h_cb + i) ^ h_x) << 4)) =
+                        make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                   *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+                }
+            }
+            fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA store
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (elected) {
+                if (EPI >= 1) {
+#pragma unroll
+                    for (int pn = 0; pn < C::NPAN; ++pn)
+                        tma_store_2d(&tmap_o32, smem_r1 + s * C::R_BYTES + pn * (BM * 128), slice * BN + pn * 32, mt * BM);
+                }
+                if (do16) tma_store_2d(&tmap_o16, smem_h + s * C::H_BYTES, slice * BN, mt * BM);
+                bulk_commit();
+                bulk_wait_read0();                          // stores have read the stage: hand it back
+                mbar_arrive(&r_empty[s]);
+            }
+        }
+        if (elected) bulk_wait0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+static size_t ws2_smem_bytes(int BN, int BK, int nseg, int nkc, int HRp, int epi, bool has_r2, bool do16) {
+    const size_t b = ((size_t)nseg * nkc * BN * BK * 2 + 1023) / 1024 * 1024;
+    const size_t a = ((size_t)nkc * HRp * BK * 2 + 1023) / 1024 * 1024;
+    size_t st = 0;
+    if (epi >= 1) st += 2 * (size_t)BM * BN * 4;
+    if (epi == 2 && has_r2) st += 2 * (size_t)BM * BN * 4;
+    if (epi < 2 || do16) st += 2 * (size_t)BM * BN * 2;
+    return b + 2 * a + st + 256 + 1024;
+}
+
+template <int BN, int BK, int EPI>
+static void ws2_launch_e(const CUtensorMap* tm, const WSParams& wp, int grid, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_ws2_kernel<BN, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    launch_pdl(gemm_ws2_kernel<BN, BK, EPI>, grid, kThreads, smem, stream, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], wp);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BK, int EPI>
@@ -411,6 +704,108 @@ static size_t ws_smem_bytes(int BN, int BK, int nseg, int nkc, int HRp) {
     return b + 2 * a + 128 + epi + 1024;
 }
 
+// v2 dispatch: the three vocoder epilogue patterns with TMA-legal operands.  Returns false to fall through to v1.
+static bool ws2_try(const GemmArgs& g, cudaStream_t stream, int BK, int nkc, int rmin, int HRp, int m_tiles, int sms, int bo_mode) {
+    static int mode = -1, n32 = 0;
+    if (mode < 0) {
+        const char* e = getenv("RVCB_WS2");
+        mode = (e && e[0] == '0') ? 0 : 1;
+        const char* f = getenv("RVCB_WS2_N32");
+        n32 = (f && f[0] == '1') ? 1 : 0;
+    }
+    if (!mode) return false;
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    if (!g.bias || !al16(g.bias) || g.act1 != ACT_NONE) return false;
+    int epi = -1;
+    if (!g.res1 && !g.res2 && !g.out32 && g.out16 && g.act2 == ACT_LRELU && g.alpha == 1.f) epi = 0;
+    else if (g.res1 && !g.res2 && g.out32 && g.out16 && g.act2 == ACT_LRELU && g.alpha == 1.f) epi = 1;
+    else if (g.res1 && g.out32 && (!g.out16 || g.act2 == ACT_LRELU)) epi = 2;
+    if (epi < 0) return false;
+    if (g.out16 && (!al16(g.out16) || g.ld16 % 8)) return false;
+    if (g.out32 && (!al16(g.out32) || g.ld32 % 4)) return false;
+    if (g.res1 && (!al16(g.res1) || g.ldres1 % 4)) return false;
+    if (g.res2 && (!al16(g.res2) || g.ldres2 % 4)) return false;
+    const bool has_r2 = g.res2 != nullptr, do16 = g.out16 != nullptr;
+    int BN = 0;
+    for (int cand : {64, 32}) {
+        if (BK == 32 && cand > 32) continue;
+        if (g.N % cand) continue;
+        if (ws2_smem_bytes(cand, BK, g.nseg, nkc, HRp, epi, has_r2, do16) <= 226 * 1024) { BN = cand; break; }
+    }
+    if (BN == 0) return false;
+    if (BN < 64 && BN < g.N && nkc > 1 && !n32) return false;      // same measured rule as v1 (override: RVCB_WS2_N32=1)
+    const int n_slices = g.N / BN;
+    if (n_slices > sms) return false;
+    const int grid = (sms / n_slices) * n_slices;
+    if ((long)m_tiles * n_slices < 4L * grid) return false;
+    WSParams wp{};
+    KParams& p = wp.k;
+    p.M = g.M; p.N = g.N; p.nseg = g.nseg; p.batch = 1;
+    for (int s = 0; s < g.nseg; ++s) {
+        p.seg[s].row = (short)g.seg[s].row_off;
+        p.seg[s].col = 0;
+        p.seg[s].nk = (short)nkc;
+        p.seg[s].dw = 0;
+    }
+    p.bias = g.bias; p.res1 = g.res1; p.ldres1 = g.ldres1; p.res2 = g.res2; p.ldres2 = g.ldres2;
+    p.alpha = g.alpha; p.act1 = g.act1; p.act1_p = g.act1_p; p.act2 = g.act2; p.act2_p = g.act2_p;
+    p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16; p.vec_ok = 1;
+    wp.rmin = rmin; wp.HRp = HRp; wp.nkc = nkc; wp.n_slices = n_slices; wp.m_tiles = m_tiles; wp.bo_mode = bo_mode;
+    wp.has_r2 = has_r2 ? 1 : 0; wp.do16 = do16 ? 1 : 0;
+
+    CUtensorMap tm[6];
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.a_cols, (cuuint64_t)g.a_rows, 1};
+        cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.lda * 2 * (cuuint64_t)g.a_rows};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)HRp, 1};
+        encode_map(&tm[0], g.A, 3, dims, str, box, BK);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.b_cols, (cuuint64_t)g.b_rows};
+        cuuint64_t str[1] = {(cuuint64_t)g.ldb * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        encode_map(&tm[1], g.B, 2, dims, str, box, BK);
+    }
+    auto map32 = [&](CUtensorMap* m, const float* base, long ld) {
+        cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+        cuuint64_t str[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+        encode_map_ex(m, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0]; tm[5] = tm[0];        // placeholders for operands a variant does not touch
+    if (g.res1) map32(&tm[2], g.res1, g.ldres1);
+    if (g.res2) map32(&tm[3], g.res2, g.ldres2);
+    if (g.out32) map32(&tm[4], g.out32, g.ld32);
+    if (g.out16) {
+        cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+        cuuint64_t str[1] = {(cuuint64_t)g.ld16 * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BN, (cuuint32_t)BM};
+        encode_map_ex(&tm[5], g.out16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, 2, dims, str, box,
+                      BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    }
+    const size_t smem = ws2_smem_bytes(BN, BK, g.nseg, nkc, HRp, epi, has_r2, do16);
+    if (gemm_prof_on()) gemm_prof_record_begin(stream);
+#define RVCB_WS2_LAUNCH(bn, bk)                                                              \
+    if (BN == bn && BK == bk) {                                                              \
+        if (epi == 0) ws2_launch_e<bn, bk, 0>(tm, wp, grid, smem, stream);                   \
+        else if (epi == 1) ws2_launch_e<bn, bk, 1>(tm, wp, grid, smem, stream);              \
+        else ws2_launch_e<bn, bk, 2>(tm, wp, grid, smem, stream);                            \
+    }
+    RVCB_WS2_LAUNCH(64, 64) RVCB_WS2_LAUNCH(32, 64) RVCB_WS2_LAUNCH(32, 32)
+#undef RVCB_WS2_LAUNCH
+    KERNEL_CHECK();
+    if (gemm_prof_on()) {
+        const double mn = (double)g.M * g.N;
+        const double bytes = (double)g.M * nkc * BK * 2 + (double)g.N * g.nseg * nkc * BK * 2 + (g.res1 ? mn * 4 : 0) + (g.res2 ? mn * 4 : 0) +
+                             (g.out32 ? mn * 4 : 0) + (g.out16 ? mn * 2 : 0);
+        ProfInfo info{g.M, g.N, g.nseg * nkc, BK, -BN /*negative = WS kernel*/, 1, g.nseg, m_tiles * n_slices};
+        info.bytes = bytes;
+        gemm_prof_record_end(stream, info);
+    }
+    count_launch();
+    return true;
+}
+
 bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
     static int mode = -1, bo_mode = 0;
     if (mode < 0) {
@@ -440,6 +835,7 @@ bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    if (ws2_try(g, stream, BK, nkc, rmin, HRp, m_tiles, sms, bo_mode)) return true;
     int BN = 0;
     for (int cand : {64, 32, 16}) {
         if (BK == 32 && cand > 32) continue;

@@ -7,6 +7,7 @@
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
 #include "gemm.cuh"
+#include <algorithm>
 #include "kernels.cuh"
 #include "weights.cuh"
 
@@ -534,8 +535,14 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             gemm(g, st);
         }
         const int nk = c.n_resblock_kernels;
-        for (int j = 0; j < nk; ++j) {
-            const ResBlock& R = S.rb[j];
+        // Branch order: widest kernel first.  The mean over branches is order-independent, and this way the branch whose
+        // resident weights are largest needs neither the running-sum tile nor the fp16 hand-off tile in shared memory.
+        int order[4] = {0, 1, 2, 3};
+        for (int a = 1; a < nk && a < 4; ++a)
+            for (int b = a; b > 0 && S.rb[order[b]].k > S.rb[order[b - 1]].k; --b) std::swap(order[b], order[b - 1]);
+        for (int jo = 0; jo < nk; ++jo) {
+            const int j = jo;                       // position in the running sum
+            const ResBlock& R = S.rb[order[jo]];
             for (int q = 0; q < 3; ++q) {
                 {
                     GemmArgs g = mk(q == 0 ? xs16 : y16, C, Tout, C, R.c1[q], Tout, C, bk);

@@ -43,6 +43,14 @@ struct KParams {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Role loops run warp-uniform and wrap only the issuing instruction in elect_one(): the
+// descriptors then live in uniform registers (an `if (lane == 0)` loop makes the compiler emit an ELECT / R2UR.BROADCAST
+// loop in front of every UTCHMMA / UTMALDG, ~27 instructions per MMA -- measured 95 cycles per 32-cycle MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -84,6 +92,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// shared -> global tile store (bulk async group); rows/columns outside the tensor map's extents are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -181,6 +197,18 @@ inline void encode_map(CUtensorMap* map, const void* base, int rank, const cuuin
     RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+
+// general form: explicit element type and swizzle (fp32 residual / output tiles of the weight-stationary kernel)
+inline void encode_map_ex(CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int elem_bytes, int rank, const cuuint64_t* dims,
+                          const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    (void)elem_bytes;
+    RVCB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    for (int i = 0; i < rank - 1; ++i) RVCB_CHECK(strides_bytes[i] % 16 == 0, "TMA stride must be a multiple of 16 bytes");
+    CUresult r = get_encode_fn()(map, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RVCB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
 
 // launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (enabled with RVCB_PDL=1)
 template <typename... KArgs, typename... Args>

@@ -295,3 +295,50 @@ def test_conv1d_weight_stationary_halo_kernel(cin, cout, k, dil, T, bk):
     _cmp("ws32", t32, ref); _cmp("simt32", s32, ref)
     _cmp("ws16", t16, F.leaky_relu(ref, 0.1), 4e-3)
     _cmp("ws-vs-simt", t32, s32, 1e-4)
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2])
+@pytest.mark.parametrize("cin,k,dil,T,bk", [(64, 11, 5, 80001, 64), (64, 3, 1, 76800, 64), (32, 7, 3, 150017, 32), (128, 3, 1, 90000, 64)])
+def test_weight_stationary_tma_epilogue_variants(epi, cin, k, dil, T, bk):
+    """The three vocoder epilogue patterns of the weight-stationary kernel's TMA-staged epilogue (gemm_ws.cu, v2):
+    0: out16 = lrelu(conv + b);  1: y = conv + b + res -> out32, out16 = lrelu(y);  2: y = (conv + b + res)/3 -> out32 only
+    (first branch of the 3-branch mean: no running sum, no fp16 hand-off).  Ragged M tails exercise the TMA store clipping;
+    the fp16 output uses a wider leading dimension, as the stage hand-off buffers do."""
+    _setup()
+    from gemm_cases import run_gemm, pack_conv1d
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(40 + epi)
+    cout = cin
+    x = torch.randn(T, cin, device=dev, generator=g).half()
+    w = (torch.randn(cout, cin, k, device=dev, generator=g) / math.sqrt(cin * k)).half()
+    bias = torch.randn(cout, device=dev, generator=g)
+    res = torch.randn(T, cout, device=dev, generator=g)
+    pad = (k - 1) * dil // 2
+    conv = F.conv1d(x.float().t()[None], w.float(), bias, dilation=dil, padding=pad)[0].t()
+    B = pack_conv1d(w, bk).contiguous()
+    segs = [(j * dil - pad, 0, 0, cin // bk) for j in range(k)]
+    ld16 = cout + 64
+
+    def run(impl):
+        o32 = torch.full((T, cout), 7.0, device=dev)
+        o16 = torch.full((T, ld16), 7.0, device=dev, dtype=torch.half)
+        if epi == 0:
+            run_gemm(impl, x, B, T, cout, segs, block_k=bk, bias=bias, act2="lrelu", act2_p=0.1, out16=o16, ld16=ld16)
+        elif epi == 1:
+            run_gemm(impl, x, B, T, cout, segs, block_k=bk, bias=bias, res1=res, act2="lrelu", act2_p=0.1, out32=o32, ld32=cout,
+                     out16=o16, ld16=ld16)
+        else:
+            run_gemm(impl, x, B, T, cout, segs, block_k=bk, bias=bias, res1=res, alpha=1.0 / 3.0, out32=o32, ld32=cout)
+        return o32, o16
+    (t32, t16), (s32, s16) = _both(run)
+    if epi == 0:
+        _cmp("ws2 c1", t16[:, :cout], F.leaky_relu(conv, 0.1), 4e-3)
+        _cmp("ws2 c1 vs simt", t16[:, :cout], s16[:, :cout], 2e-3)
+    else:
+        y = conv + res if epi == 1 else (conv + res) / 3.0
+        _cmp("ws2 y", t32, y); _cmp("ws2 vs simt", t32, s32, 1e-4)
+        if epi == 1:
+            _cmp("ws2 y16", t16[:, :cout], F.leaky_relu(y, 0.1), 4e-3)
+    assert (t16[:, cout:] == 7.0).all(), "columns past N of the fp16 hand-off buffer must not be touched"
+    if epi == 0:
+        assert (t32 == 7.0).all()
