@@ -287,10 +287,10 @@ def main():
         "data": "synthetic", "rtf_x_per_gpu": value / world / 48000.0,
         "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)",
                    "l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1,
-                   "device_step": "CUDA graph replay of the 487-launch step" if use_graph else "eager launches"},
-        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(2 * 256000 * 4 + 160000 * 4 + 1598 * 12 + 8),   # audio_pad (f0 + HuBERT), audio (RMS mix), pitch/pitchf
-                "d2h_bytes_per_step": int(OUT_SAMPLES * 4 + 1601 * 4),                      # mixed + normalised waveform, f0 track
-                "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0, "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
+                   "device_step": f"CUDA graph replay of the {int(launches)}-launch step" if use_graph else "eager launches"},
+        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(160000 * 4 + 8),   # the utterance (float32, one pinned copy) + speaker id
+                "d2h_bytes_per_step": int(OUT_SAMPLES * 2),  # mixed + normalised waveform, int16
+                "ms_per_step": e2e_ms / args.steps, "rtf_x_per_gpu": e2e_v / world / 48000.0,
                 "api": "infer.modules.vc.VC.vc_single (host numpy in, host int16 out)"},
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),

@@ -11,6 +11,7 @@ static thread_local std::string g_err;
 void set_last_error(const std::string& s) { g_err = s; }
 }  // namespace rvcb
 
+#include <vector>
 #include "api_macros.h"
 
 extern "C" {
@@ -102,6 +103,85 @@ extern "C" int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const floa
     RVCB_API_BEGIN
     RVCB_CHECK(d_wav && d_audio16k && d_scratch && n_out > 0 && n_in > 0 && tgt_sr >= 16000, "bad argument");
     rvcb::post_mix(d_wav, n_out, tgt_sr, d_audio16k, n_in, rms_mix_rate, d_scratch, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+// scipy.signal.lfilter's float64 loop (direct form II transposed), one pass; z is the state, updated in place
+static void lfilter_df2t(const double* b, const double* a, int nc, const double* x, int64_t n, int64_t stride, double* y, double* z) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double xi = x[i * stride];
+        const double yi = z[0] + b[0] * xi;
+        for (int k = 1; k < nc - 1; ++k) z[k - 1] = z[k] + xi * b[k] - yi * a[k];
+        z[nc - 2] = xi * b[nc - 1] - yi * a[nc - 1];
+        y[i * stride] = yi;
+    }
+}
+
+extern "C" int rvcb_host_filtfilt(const double* b, const double* a, const double* zi, int ncoef, const void* xv, int x_is_f32, int64_t n,
+                                  double* y) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(b && a && zi && xv && y && ncoef >= 2 && ncoef <= 16 && a[0] == 1.0, "bad filter");
+    const int64_t edge = 3 * (int64_t)ncoef;
+    RVCB_CHECK(n > edge, "The length of the input vector x must be greater than padlen");
+    // odd extension: 2*x[0] - x[edge..1], x, 2*x[n-1] - x[n-2..n-edge-1]   (in the input's own precision, as numpy does)
+    std::vector<double> ext((size_t)(n + 2 * edge));
+    if (x_is_f32) {
+        const float* x = static_cast<const float*>(xv);
+        for (int64_t i = 0; i < edge; ++i) ext[(size_t)i] = (double)(float)(2.0f * x[0] - x[edge - i]);
+        for (int64_t i = 0; i < n; ++i) ext[(size_t)(edge + i)] = (double)x[i];
+        for (int64_t i = 0; i < edge; ++i) ext[(size_t)(edge + n + i)] = (double)(float)(2.0f * x[n - 1] - x[n - 2 - i]);
+    } else {
+        const double* x = static_cast<const double*>(xv);
+        for (int64_t i = 0; i < edge; ++i) ext[(size_t)i] = 2.0 * x[0] - x[edge - i];
+        for (int64_t i = 0; i < n; ++i) ext[(size_t)(edge + i)] = x[i];
+        for (int64_t i = 0; i < edge; ++i) ext[(size_t)(edge + n + i)] = 2.0 * x[n - 1] - x[n - 2 - i];
+    }
+    const int64_t m = n + 2 * edge;
+    double z[16];
+    for (int k = 0; k < ncoef - 1; ++k) z[k] = zi[k] * ext[0];
+    lfilter_df2t(b, a, ncoef, ext.data(), m, 1, ext.data(), z);                 // forward
+    for (int k = 0; k < ncoef - 1; ++k) z[k] = zi[k] * ext[(size_t)(m - 1)];
+    lfilter_df2t(b, a, ncoef, ext.data() + (m - 1), m, -1, ext.data() + (m - 1), z);   // backward, in place
+    for (int64_t i = 0; i < n; ++i) y[i] = ext[(size_t)(edge + i)];
+    RVCB_API_END
+}
+
+extern "C" int rvcb_sosfiltfilt(const double* sos, const double* zi, int n_sections, int edge, const float* d_x, int64_t n, float* d_y,
+                                double* d_scratch, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(sos && zi && d_x && d_y && d_scratch, "null argument");
+    RVCB_CHECK(n_sections >= 1 && n_sections <= 4, "rvcb_sosfiltfilt: 1..4 sections");
+    rvcb::SosCoef c{};
+    c.ns = n_sections;
+    for (int s = 0; s < n_sections; ++s) {
+        RVCB_CHECK(sos[s * 6 + 3] == 1.0, "rvcb_sosfiltfilt: sections must be normalised (a0 == 1)");
+        for (int k = 0; k < 6; ++k) c.sos[s][k] = sos[s * 6 + k];
+        c.zi[s][0] = zi[s * 2];
+        c.zi[s][1] = zi[s * 2 + 1];
+    }
+    rvcb::sosfiltfilt(c, d_x, n, edge, d_y, d_scratch, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+extern "C" int rvcb_reflect_pad(const float* d_x, int64_t n, int64_t pad, float* d_out, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_x && d_out && n > 0, "bad argument");
+    rvcb::reflect_pad(d_x, n, pad, d_out, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+extern "C" int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_x && d_out && n > 0, "bad argument");
+    rvcb::f32_to_i16(d_x, n, d_out, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+extern "C" int rvcb_f0_post(const float* d_f0, int n_frames, int p_len, double key_factor, double f0_min, double f0_max, int64_t* d_pitch,
+                            float* d_pitchf, double* d_scratch, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_f0 && d_pitch && d_pitchf && d_scratch, "null argument");
+    rvcb::f0_post(d_f0, n_frames, p_len, key_factor, f0_min, f0_max, (long long*)d_pitch, d_pitchf, d_scratch, (cudaStream_t)stream);
     RVCB_API_END
 }
 

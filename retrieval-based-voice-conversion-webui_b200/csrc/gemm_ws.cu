@@ -380,7 +380,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 //   * the producer prefetches the fp32 residual tile(s) of tile i+1 into swizzled shared memory while tile i computes;
 //   * the 8 epilogue warps go TMEM -> registers -> (+bias, +residual from smem) -> write y (fp32, in place over the residual
 //     tile) and lrelu(y) (fp16) back to shared memory -- no global loads or stores, no exposed HBM latency;
-//   * one elected thread issues the tile stores (cp.async.bulk.tensor, clipped at M) and frees the staging stage.
+//   * the producer warp (lane 0) stores each finished tile (cp.async.bulk.tensor, clipped at M), drains the stage and reuses
+//     it for the next residual prefetch; the epilogue warps never wait on a store and need no block-wide barrier.
 // Staging tiles use the TMA 128 B / 64 B swizzle, so "thread = row" 16-byte accesses are bank-conflict free.
 // EPI as above (0: c1, 1: c2, 2: last c2 of a resblock); the generic contract stays on the v1 kernel.
 // ------------------------------------------------------------------------------------------------
@@ -424,8 +425,9 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint64_t* tfull_bar = bars + 5;     // [2]
     uint64_t* tempty_bar = bars + 7;    // [2]
     uint64_t* r_full = bars + 9;        // [2] residual tile(s) landed
-    uint64_t* r_empty = bars + 11;      // [2] staging stage drained by the TMA stores
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* r_empty = bars + 11;      // [2] staging stage drained by the TMA stores (EPI 0 only: nothing else tells the epilogue)
+    uint64_t* s_full = bars + 13;       // [2] epilogue warps finished writing the staging stage
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -444,6 +446,7 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             mbar_init(&tempty_bar[i], kEpiWarps);
             mbar_init(&r_full[i], 1);
             mbar_init(&r_empty[i], 1);
+            mbar_init(&s_full[i], kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -460,38 +463,65 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int mt_step = gridDim.x / wp.n_slices;
 
     if (warp == 0) {
-        // ======================= TMA producer (warp-uniform loop, one elected lane issues) =======================
-        if (elect_one()) {
+        // ======================= TMA producer + store issuer =======================
+        // Warp-uniform loop; lane 0 issues (bulk async groups are per thread, so the same lane must issue and drain the stores).
+        // Iteration `it`: prefetch the halo tile of tile it+1; load the residual of tile `it` (its stage was drained at the end
+        // of the previous iteration); then, once the epilogue warps have written tile it-1, store it and drain the stage.
+        const int n_it = (wp.m_tiles - mt0 + mt_step - 1) / mt_step;
+        auto load_a = [&](int it) {
+            const int buf = it & 1;
+            mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_expect_tx(&a_full[buf], (uint32_t)(wp.nkc * a_chunk));
+                for (int kc = 0; kc < wp.nkc; ++kc)
+                    tma_load_3d(smem_a + buf * a_buf + kc * a_chunk, &tmap_a, &a_full[buf], kc * BK, (mt0 + it * mt_step) * BM + wp.rmin, 0);
+            }
+            __syncwarp();
+        };
+        auto store_tile = [&](int it) {
+            const int s = it & 1;
+            const int m0 = (mt0 + it * mt_step) * BM;
+            mbar_wait(&s_full[s], (it >> 1) & 1);
+            if (lane == 0) {
+                if (EPI >= 1) {
+#pragma unroll
+                    for (int pn = 0; pn < C::NPAN; ++pn)
+                        tma_store_2d(&tmap_o32, smem_r1 + s * C::R_BYTES + pn * (BM * 128), slice * BN + pn * 32, m0);
+                }
+                if (do16) tma_store_2d(&tmap_o16, smem_h + s * C::H_BYTES, slice * BN, m0);
+                bulk_commit();
+                bulk_wait_read0();                          // the stores have read the stage
+                if (EPI == 0) mbar_arrive(&r_empty[s]);     // EPI >= 1: the next residual load into this stage is the signal
+            }
+            __syncwarp();
+        };
+        if (lane == 0) {
             mbar_expect_tx(b_full, (uint32_t)b_bytes);
             for (int kb = 0; kb < total_kb; ++kb)
                 tma_load_2d(smem_b + kb * B_KB_BYTES, &tmap_b, b_full, kb * BK, slice * BN);
         }
         __syncwarp();
-        int it = 0;
-        for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(&a_empty[buf], ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&a_full[buf], (uint32_t)(wp.nkc * a_chunk));
-                for (int kc = 0; kc < wp.nkc; ++kc)
-                    tma_load_3d(smem_a + buf * a_buf + kc * a_chunk, &tmap_a, &a_full[buf], kc * BK, mt * BM + wp.rmin, 0);
-            }
-            __syncwarp();
+        if (n_it > 0) load_a(0);
+        for (int it = 0; it < n_it; ++it) {
+            if (it + 1 < n_it) load_a(it + 1);
             if (EPI >= 1) {
-                mbar_wait(&r_empty[buf], ph ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(&r_full[buf], (uint32_t)(C::R_BYTES * (has_r2 ? 2 : 1)));
+                const int s = it & 1;
+                if (lane == 0) {
+                    const int m0 = (mt0 + it * mt_step) * BM;
+                    mbar_expect_tx(&r_full[s], (uint32_t)(C::R_BYTES * (has_r2 ? 2 : 1)));
 #pragma unroll
                     for (int pn = 0; pn < C::NPAN; ++pn) {
-                        tma_load_2d(smem_r1 + buf * C::R_BYTES + pn * (BM * 128), &tmap_r1, &r_full[buf], slice * BN + pn * 32, mt * BM);
-                        if (has_r2)
-                            tma_load_2d(smem_r2 + buf * C::R_BYTES + pn * (BM * 128), &tmap_r2, &r_full[buf], slice * BN + pn * 32, mt * BM);
+                        tma_load_2d(smem_r1 + s * C::R_BYTES + pn * (BM * 128), &tmap_r1, &r_full[s], slice * BN + pn * 32, m0);
+                        if (has_r2) tma_load_2d(smem_r2 + s * C::R_BYTES + pn * (BM * 128), &tmap_r2, &r_full[s], slice * BN + pn * 32, m0);
                     }
                 }
                 __syncwarp();
             }
+            if (it >= 1) store_tile(it - 1);
         }
+        if (n_it > 0) store_tile(n_it - 1);
+        if (lane == 0) bulk_wait0();
+        __syncwarp();
     } else if (warp == 1) {
         // ======================= MMA issuer (warp-uniform loop, one elected lane issues) =======================
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -553,7 +583,6 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             bias_r[i] = b.x; bias_r[i + 1] = b.y; bias_r[i + 2] = b.z; bias_r[i + 3] = b.w;
         }
         const float slope = p.act2_p, alpha = p.alpha;
-        const bool elected = (warp == 2 && lane == 0);
         int it = 0;
         for (int mt = mt0; mt < wp.m_tiles; mt += mt_step, ++it) {
             const int s = it & 1;
@@ -616,20 +645,9 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
             }
             fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA store
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (elected) {
-                if (EPI >= 1) {
-#pragma unroll
-                    for (int pn = 0; pn < C::NPAN; ++pn)
-                        tma_store_2d(&tmap_o32, smem_r1 + s * C::R_BYTES + pn * (BM * 128), slice * BN + pn * 32, mt * BM);
-                }
-                if (do16) tma_store_2d(&tmap_o16, smem_h + s * C::H_BYTES, slice * BN, mt * BM);
-                bulk_commit();
-                bulk_wait_read0();                          // stores have read the stage: hand it back
-                mbar_arrive(&r_empty[s]);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);        // warp 0 stores the tile once all 8 warps have arrived
         }
-        if (elected) bulk_wait0();
     }
 
     tc_fence_before();

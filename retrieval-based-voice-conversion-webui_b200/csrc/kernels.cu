@@ -621,4 +621,212 @@ void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long
     count_launch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// input / output plumbing kernels
+// ------------------------------------------------------------------------------------------------
+// Forward-backward IIR (scipy filtfilt semantics: odd extension by `edge` samples, steady-state edge conditions) on ONE CTA,
+// as a cascade of second-order sections.  The 5th-order direct form of the reference has poles clustered at |z| = 0.98..0.994;
+// its 5x5 state matrix is too non-normal to propagate across blocks in float64 (A^L computed to ~1e13 instead of ~1), the 2x2
+// section matrices are benign (|A^L| <= ~30).  Per section and direction, each of the 256 threads owns a block of L samples:
+//   pass 1  zero-state run over the block -> its end state                      (parallel)
+//   scan    true start state of every block: s <- A^L s + end_state             (thread 0; A^L by repeated squaring)
+//   pass 2  exact re-run of the block from its start state, writing y in place  (parallel)
+// DF2T section: y = z0 + b0 x;  z0' = z1 + b1 x - a1 y;  z1' = b2 x - a2 y;   A = [[-a1, 1], [-a2, 0]].
+constexpr int IIR_T = 512, IIR_B = 16;      // threads (= blocks of the recurrence), samples fetched per batch
+__device__ __forceinline__ double sos_step(double& z0, double& z1, const double* c, double x) {
+    const double y = z0 + c[0] * x;
+    z0 = z1 + c[1] * x - c[4] * y;
+    z1 = c[2] * x - c[5] * y;
+    return y;
+}
+__global__ void __launch_bounds__(IIR_T) sosfiltfilt_kernel(const SosCoef c, const float* __restrict__ x, long n, int edge,
+                                                            float* __restrict__ out, double* __restrict__ w) {
+    __shared__ double s_st[IIR_T][2];      // zero-state end state of each block, then its true start state
+    const long m = n + 2L * edge;
+    const long L = (m + IIR_T - 1) / IIR_T;
+    const int t = threadIdx.x;
+    const long lo = (long)t * L, hi = min(lo + L, m);
+    auto ext = [&](long i) -> double {     // odd extension, formed in float32 like numpy does on float32 audio
+        if (i < edge) return (double)__fsub_rn(2.0f * x[0], x[edge - i]);
+        if (i < edge + n) return (double)x[i - edge];
+        return (double)__fsub_rn(2.0f * x[n - 1], x[n - 2 - (i - edge - n)]);
+    };
+    __shared__ double x0s;                 // first sample of the cascade's input in this direction (edge condition)
+    for (int dir = 0; dir < 2; ++dir) {
+        if (t == 0) x0s = (dir == 0) ? ext(0) : w[m - 1];
+        __syncthreads();
+        for (int sec = 0; sec < c.ns; ++sec) {
+            const double* q = c.sos[sec];
+            const bool first = (dir == 0 && sec == 0);
+            auto in = [&](long i) -> double { return first ? ext(i) : w[dir == 0 ? i : m - 1 - i]; };
+            {   // pass 1 (samples are fetched IIR_B at a time so their load latencies overlap; the recurrence then runs from registers)
+                double z0 = 0.0, z1 = 0.0;
+                if (hi - lo == L) {
+                    for (long i0 = lo; i0 < hi; i0 += IIR_B) {
+                        double v[IIR_B];
+#pragma unroll
+                        for (int k = 0; k < IIR_B; ++k) v[k] = (i0 + k < hi) ? in(i0 + k) : 0.0;
+#pragma unroll
+                        for (int k = 0; k < IIR_B; ++k)
+                            if (i0 + k < hi) sos_step(z0, z1, q, v[k]);
+                    }
+                }
+                s_st[t][0] = z0; s_st[t][1] = z1;
+            }
+            __syncthreads();
+            if (t == 0) {
+                double p00 = -q[4], p01 = 1.0, p10 = -q[5], p11 = 0.0;      // P = A
+                double r00 = 1.0, r01 = 0.0, r10 = 0.0, r11 = 1.0;          // R = I
+                for (long e = L; e > 0; e >>= 1) {
+                    if (e & 1) {
+                        const double a = r00 * p00 + r01 * p10, b = r00 * p01 + r01 * p11;
+                        const double cc = r10 * p00 + r11 * p10, d = r10 * p01 + r11 * p11;
+                        r00 = a; r01 = b; r10 = cc; r11 = d;
+                    }
+                    const double a = p00 * p00 + p01 * p10, b = p00 * p01 + p01 * p11;
+                    const double cc = p10 * p00 + p11 * p10, d = p10 * p01 + p11 * p11;
+                    p00 = a; p01 = b; p10 = cc; p11 = d;
+                }
+                // edge condition: the cascade has been fed its first input sample forever (sosfilt_zi is per unit input level)
+                double s0 = c.zi[sec][0] * x0s, s1 = c.zi[sec][1] * x0s;
+                for (int bq = 0; bq < IIR_T; ++bq) {
+                    const double n0 = r00 * s0 + r01 * s1 + s_st[bq][0];
+                    const double n1 = r10 * s0 + r11 * s1 + s_st[bq][1];
+                    s_st[bq][0] = s0; s_st[bq][1] = s1;
+                    s0 = n0; s1 = n1;
+                }
+            }
+            __syncthreads();
+            {   // pass 2: every thread reads and writes only its own block (in place from the second pass on)
+                double z0 = s_st[t][0], z1 = s_st[t][1];
+                for (long i0 = lo; i0 < hi; i0 += IIR_B) {
+                    double v[IIR_B];
+#pragma unroll
+                    for (int k = 0; k < IIR_B; ++k) v[k] = (i0 + k < hi) ? in(i0 + k) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < IIR_B; ++k)
+                        if (i0 + k < hi) w[dir == 0 ? i0 + k : m - 1 - (i0 + k)] = sos_step(z0, z1, q, v[k]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (long i = t; i < n; i += IIR_T) out[i] = (float)w[edge + i];
+}
+void sosfiltfilt(const SosCoef& c, const float* x, long n, int edge, float* y, double* scratch, cudaStream_t s) {
+    RVCB_CHECK(c.ns >= 1 && c.ns <= 4 && edge >= 0, "sosfiltfilt: 1..4 sections");
+    RVCB_CHECK(n > edge, "The length of the input vector x must be greater than padlen");
+    sosfiltfilt_kernel<<<1, IIR_T, 0, s>>>(c, x, n, edge, y, scratch);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+__global__ void reflect_pad_1d_kernel(const float* __restrict__ x, long n, long pad, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + 2 * pad) return;
+    long j = i - pad;
+    if (j < 0) j = -j;
+    else if (j >= n) j = 2 * (n - 1) - j;
+    out[i] = x[j];
+}
+void reflect_pad(const float* x, long n, long pad, float* out, cudaStream_t s) {
+    RVCB_CHECK(pad >= 0 && pad < n, "reflect_pad: pad must be smaller than the signal");
+    reflect_pad_1d_kernel<<<(unsigned)ceil_div_l(n + 2 * pad, 256), 256, 0, s>>>(x, n, pad, out);
+    KERNEL_CHECK();
+    count_launch();
+}
+__global__ void f32_to_i16_kernel(const float* __restrict__ x, long n, short* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (short)__float2int_rz(x[i]);
+}
+void f32_to_i16(const float* x, long n, short* out, cudaStream_t s) {
+    f32_to_i16_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(x, n, out);
+    KERNEL_CHECK();
+    count_launch();
+}
+
+// f0 post-processing, one block.  Phase 1 (parallel): resize by np.interp over the NaN-marked contour (compiled_base.c
+// arr_interp: exact-hit shortcut, slope*(x - xp[j]) + fp[j], the two NaN fallbacks), NaN -> 0.  Phase 2 (thread 0): the
+// gap fill of F0Predictor._interpolate_f0 as a run scan.  Phase 3 (parallel): key shift and mel quantisation of
+// post_process.  All float64 with explicit round-to-nearest mul/add (no FMA contraction), i.e. numpy's arithmetic.
+__global__ void __launch_bounds__(256) f0_post_kernel(const float* __restrict__ f0, int L, int n, double key_factor, double mel_min,
+                                                      double mel_max, long long* __restrict__ pitch, float* __restrict__ pitchf,
+                                                      double* __restrict__ data) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto src = [&](int j) -> double {
+        const double v = (double)f0[j];
+        return v < 0.001 ? qnan : v;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = (double)((long long)i * L) / (double)n;
+        double r;
+        if (x > (double)(L - 1)) {
+            r = src(L - 1);
+        } else {
+            const int j = (int)x;                      // xp = arange(L): the bracketing index is floor(x)
+            if (j == L - 1 || (double)j == x) {
+                r = src(j);
+            } else {
+                const double y0 = src(j), y1 = src(j + 1);
+                const double slope = __ddiv_rn(__dsub_rn(y1, y0), 1.0);
+                r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, (double)j)), y0);
+                if (isnan(r)) {
+                    r = __dadd_rn(__dmul_rn(slope, __dsub_rn(x, (double)(j + 1))), y1);
+                    if (isnan(r) && y0 == y1) r = y0;
+                }
+            }
+        }
+        data[i] = isnan(r) ? 0.0 : r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int i = 0;
+        double last_value = 0.0;
+        while (i < n) {
+            if (data[i] > 0.0) {
+                last_value = data[i];
+                ++i;
+                continue;
+            }
+            int j = i + 1;
+            while (j < n && !(data[j] > 0.0)) ++j;
+            const int jj = j < n ? j : (i + 1 < n ? n - 1 : i + 1);
+            if (jj < n - 1) {
+                if (last_value > 0.0) {
+                    const double base = data[i - 1];
+                    const double step = __ddiv_rn(__dsub_rn(data[jj], base), (double)(jj - i));
+                    for (int k = i; k < jj; ++k) data[k] = __dadd_rn(base, __dmul_rn(step, (double)(k - i + 1)));
+                } else {
+                    const double v = data[jj];
+                    for (int k = i; k < jj; ++k) data[k] = v;
+                }
+                if (jj > i) last_value = data[jj - 1];
+                i = jj;
+            } else {
+                for (int k = i; k < n; ++k) data[k] = last_value;
+                i = n;
+            }
+        }
+    }
+    __syncthreads();
+    const double span = __dsub_rn(mel_max, mel_min);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double f = __dmul_rn(data[i], key_factor);
+        double mel = __dmul_rn(1127.0, log(__dadd_rn(1.0, __ddiv_rn(f, 700.0))));
+        if (mel > 0.0) mel = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(mel, mel_min), 254.0), span), 1.0);
+        if (mel <= 1.0) mel = 1.0;
+        if (mel > 255.0) mel = 255.0;
+        pitch[i] = (long long)rint(mel);
+        pitchf[i] = (float)f;
+    }
+}
+void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double f0_min, double f0_max, long long* pitch, float* pitchf,
+             double* scratch, cudaStream_t s) {
+    RVCB_CHECK(n_frames >= 1 && p_len >= 1, "f0_post: empty contour");
+    const double mel_min = 1127.0 * std::log(1.0 + f0_min / 700.0), mel_max = 1127.0 * std::log(1.0 + f0_max / 700.0);
+    f0_post_kernel<<<1, 256, 0, s>>>(f0, n_frames, p_len, key_factor, mel_min, mel_max, pitch, pitchf, scratch);
+    KERNEL_CHECK();
+    count_launch();
+}
+
 }  // namespace rvcb

@@ -57,4 +57,15 @@ void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate
 // fp32 SIMT GEMM  C[M,N] = A[M,K] * B[N,K]^T  (A rows may overlap: lda < K is allowed)
 void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, cudaStream_t s);
 
+// forward-backward IIR as a cascade of <= 4 second-order sections [b0 b1 b2 1 a1 a2] (odd extension by `edge` samples,
+// edge state zi[sec] * first input sample), float64, block-parallel on one CTA
+struct SosCoef { int ns; double sos[4][6]; double zi[4][2]; };
+void sosfiltfilt(const SosCoef& c, const float* x, long n, int edge, float* y, double* scratch, cudaStream_t s);
+// np.pad(mode="reflect") of a 1-D signal
+void reflect_pad(const float* x, long n, long pad, float* out, cudaStream_t s);
+void f32_to_i16(const float* x, long n, short* out, cudaStream_t s);
+// resize (np.interp with unvoiced -> NaN -> 0) + gap fill + key shift + mel quantisation, float64, numpy operation order
+void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double f0_min, double f0_max, long long* pitch, float* pitchf,
+             double* scratch, cudaStream_t s);
+
 }  // namespace rvcb

@@ -35,6 +35,7 @@ class RVC:
         self.cache_pitchf = torch.zeros(1024, device=self.device, dtype=torch.float32)
         self.resample_kernel = {}
         self._side = torch.cuda.Stream(device=self.device)
+        self._graphs = {}
         self.f0_gen = Generator(rmvpe_state_dict or Path(os.environ.get("rmvpe_root", "assets/rmvpe")), is_half, 0, self.device,
                                 self.window, self.sr)
         self.hubert = hubert_model if hubert_model is not None else load_hubert(self.device, is_half)
@@ -64,9 +65,37 @@ class RVC:
     @torch.no_grad()
     def infer(self, input_wav: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method: Union[tuple, str],
               protect: float = 1.0) -> torch.Tensor:
+        """rtrvc.py:131-246.  A realtime session calls this with the same shapes block after block: from the second block with
+        the same (shapes, settings) on, the whole block -- both streams, the pitch-cache roll, the noise draws -- is one CUDA
+        graph replay (RVCB_GRAPHS=0 turns that off)."""
         wav_dev = input_wav.float().to(self.device)
         if wav_dev.dim() == 2:
             wav_dev = wav_dev.mean(-1)
+        key = None
+        if isinstance(f0method, str) and os.environ.get("RVCB_GRAPHS", "1") != "0" and getattr(self.net_g, "accepts_host_scalars", False):
+            key = (int(wav_dev.shape[0]), int(block_frame_16k), int(skip_head), int(return_length), f0method, float(protect),
+                   float(self.f0_up_key), float(self.formant_shift), float(self.index_rate), id(getattr(self, "index", None)))
+        ent = self._graphs.get(key) if key is not None else None
+        if ent is None:
+            if key is not None:
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = {}
+            return self._infer_body(wav_dev, block_frame_16k, skip_head, return_length, f0method, protect)
+        if "graph" not in ent:
+            ent["x"] = torch.empty_like(wav_dev)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = self._infer_body(ent["x"], block_frame_16k, skip_head, return_length, f0method, protect)
+            ent["graph"] = g
+        ent["x"].copy_(wav_dev, non_blocking=True)
+        ent["graph"].replay()
+        return ent["out"].clone()
+
+    def _infer_body(self, wav_dev: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method, protect: float):
+        input_wav = wav_dev
+        capturing = torch.cuda.is_current_stream_capturing()
         # content features + retrieval do not depend on f0: run them on a side stream while RMVPE runs on the main one
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
@@ -100,9 +129,14 @@ class RVC:
             f0_extractor_frame = block_frame_16k + 800
             if f0method == "rmvpe":
                 f0_extractor_frame = 5120 * ((f0_extractor_frame - 1) // 5120 + 1) - self.window
-            c, f = self.f0_gen.calculate(input_wav[-f0_extractor_frame:], None, self.f0_up_key - self.formant_shift, f0method, None)
-            pitch = torch.from_numpy(c).long().to(self.device)
-            pitchf = torch.from_numpy(np.asarray(f)).float().to(self.device)
+            wav_f0 = input_wav[-f0_extractor_frame:]
+            if f0method == "rmvpe" and torch.is_tensor(wav_f0) and wav_f0.is_cuda:
+                # RMVPE + f0 post-processing stay on the device: no host round trip inside the block
+                pitch, pitchf = self.f0_gen.calculate_device(wav_f0, wav_f0.shape[0] // self.window, self.f0_up_key - self.formant_shift)
+            else:
+                c, f = self.f0_gen.calculate(wav_f0, None, self.f0_up_key - self.formant_shift, f0method, None)
+                pitch = torch.from_numpy(c).long().to(self.device)
+                pitchf = torch.from_numpy(np.asarray(f)).float().to(self.device)
             shift = block_frame_16k // self.window
             self.cache_pitch[:-shift] = self.cache_pitch[shift:].clone()
             self.cache_pitchf[:-shift] = self.cache_pitchf[shift:].clone()
@@ -111,9 +145,10 @@ class RVC:
             cache_pitch = self.cache_pitch[None, -p_len:]
             cache_pitchf = self.cache_pitchf[None, -p_len:] * return_length2 / return_length
         cur.wait_event(feats_ready)
-        feats.record_stream(cur)
-        if feats0 is not None:
-            feats0.record_stream(cur)
+        if not capturing:
+            feats.record_stream(cur)
+            if feats0 is not None:
+                feats0.record_stream(cur)
         use_protect = protect < 0.5 and pitch is not None and pitchf is not None and feats0 is not None
         pf = None
         if use_protect:
@@ -121,7 +156,7 @@ class RVC:
             n = min(p_len, pitchf.reshape(-1).shape[0])
             pf[:n] = pitchf.reshape(-1)[:n]
         phone = engine.upsample_protect(feats, feats0 if use_protect else None, pf, p_len, protect if use_protect else 1.0)
-        out = self.net_g.infer(phone.unsqueeze(0), torch.tensor([p_len], device=self.device), torch.tensor([0], device=self.device),
+        out = self.net_g.infer(phone.unsqueeze(0), torch.tensor([p_len]), torch.tensor([0]),     # host scalars: no stream sync
                                pitch=cache_pitch, pitchf=cache_pitchf, skip_head=skip_head, return_length=return_length,
                                return_length2=return_length2).squeeze(1).float()
         upp_res = int(np.floor(factor * self.tgt_sr // 100))

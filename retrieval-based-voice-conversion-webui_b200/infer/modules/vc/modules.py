@@ -89,9 +89,13 @@ class VC:
                 file_index = file_index2
             else:
                 file_index = ""
-            audio_opt = self.pipeline.pipeline(self.hubert_model, self.net_g, sid, audio, times, f0_up_key, f0_method, file_index,
-                                               index_rate, self.if_f0, filter_radius, self.tgt_sr, resample_sr, rms_mix_rate,
-                                               self.version, protect, f0_file).astype(np.int16)
+            self.pipeline._want_int16 = True        # the device path casts like .astype(np.int16) before its single D2H copy
+            try:
+                audio_opt = self.pipeline.pipeline(self.hubert_model, self.net_g, sid, audio, times, f0_up_key, f0_method, file_index,
+                                                   index_rate, self.if_f0, filter_radius, self.tgt_sr, resample_sr, rms_mix_rate,
+                                                   self.version, protect, f0_file).astype(np.int16, copy=False)
+            finally:
+                self.pipeline._want_int16 = False
             tgt_sr = resample_sr if self.tgt_sr != resample_sr >= 16000 else self.tgt_sr
             index_info = ("Index: %s." % file_index if (not isinstance(file_index, str) or os.path.exists(file_index)) else "Index not used.")
             return ("Success.\n%s\nTime: npy: %.2fs, f0: %.2fs, infer: %.2fs." % (index_info, *times), (tgt_sr, audio_opt))

@@ -24,6 +24,8 @@ from rvc_b200 import engine, faiss_io
 logger = logging.getLogger(__name__)
 
 bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)     # pipeline.py:23
+zi_h = signal.lfilter_zi(bh, ah)                                # filtfilt's edge state, a constant of the filter
+sos_h, sos_zi_h = engine.highpass_sos_from_ba(bh, ah)            # the same filter as second-order sections (device path)
 
 
 def _rms(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray:
@@ -69,11 +71,13 @@ class Pipeline(object):
         self._index_cache = {}
         self._side = torch.cuda.Stream(device=self.device)
         self._prefetched = None
+        self._pinned = None          # reusable pinned staging buffer for the H2D copy of the utterance
+        self._graphs = {}            # (length, settings) -> captured CUDA graph of the device-resident utterance path
 
     # -----------------------------------------------------------------------------------------
     def _features(self, model, audio0, index, big_npy, index_rate, version):
         """HuBERT features (+ IVF-Flat blend) of one chunk: (blended [T_h, C], unblended [T_h, C])"""
-        feats = torch.from_numpy(np.ascontiguousarray(audio0, dtype=np.float32))
+        feats = audio0.float() if torch.is_tensor(audio0) else torch.from_numpy(np.ascontiguousarray(audio0, dtype=np.float32))
         if feats.dim() == 2:
             feats = feats.mean(-1)
         assert feats.dim() == 1, feats.dim()
@@ -110,8 +114,9 @@ class Pipeline(object):
             _, f, f_raw, ev = self._prefetched          # computed on the side stream while RMVPE was running
             self._prefetched = None
             torch.cuda.current_stream().wait_event(ev)
-            f.record_stream(torch.cuda.current_stream())
-            f_raw.record_stream(torch.cuda.current_stream())
+            if not torch.cuda.is_current_stream_capturing():
+                f.record_stream(torch.cuda.current_stream())
+                f_raw.record_stream(torch.cuda.current_stream())
         else:
             f, f_raw = self._features(model, audio0, index, big_npy, index_rate, version)
         use_protect = protect < 0.5 and pitch is not None and pitchf is not None
@@ -135,7 +140,8 @@ class Pipeline(object):
             if pitch is not None and pitch.shape[1] < T:      # masks use p_len; frames past it are ignored downstream
                 phone = phone[: pitch.shape[1]]
                 T = phone.shape[0]
-            audio1 = net_g.infer(phone.unsqueeze(0), torch.tensor([T], device=self.device), sid,
+            host_ok = getattr(net_g, "accepts_host_scalars", False)      # a device tensor here costs a stream sync (.item())
+            audio1 = net_g.infer(phone.unsqueeze(0), torch.tensor([T]) if host_ok else torch.tensor([T], device=self.device), sid,
                                  pitch=None if pitch is None else pitch[:, :T], pitchf=None if pitchf is None else pitchf[:, :T])[0, 0]
         t2 = time()
         times[0] += t1 - t0
@@ -155,6 +161,80 @@ class Pipeline(object):
         ix = self._index_cache[key]
         return ix, ix.vectors
 
+    def _stage_h2d(self, audio: np.ndarray) -> torch.Tensor:
+        """One pinned-memory H2D copy of the utterance (float32), asynchronous on the current stream."""
+        n = int(audio.shape[0])
+        if self._pinned is None or self._pinned.numel() < n:
+            self._pinned = torch.empty(max(n, 1 << 18), dtype=torch.float32, pin_memory=True)
+        stage = self._pinned[:n]
+        stage.numpy()[:] = audio          # casts float64 -> float32 if needed
+        return stage.to(self.device, non_blocking=True)
+
+    def _dev_body(self, x, model, net_g, sid, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version,
+                  protect, as_int16):
+        """Device-resident body of one single-chunk utterance: x f32[n] (device) -> waveform (device).  No host
+        synchronisation anywhere, so it can run eagerly or be captured once into a CUDA graph and replayed."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        a16 = engine.sosfiltfilt(sos_h, sos_zi_h, 3 * max(len(ah), len(bh)), x)
+        audio_pad = engine.reflect_pad(a16, self.t_pad)
+        p_len = audio_pad.numel() // self.window
+        pitch = pitchf = None
+        self._prefetched = None
+        if if_f0 == 1:
+            cur = torch.cuda.current_stream()
+            # f0 first: RMVPE has the fewer launches, so both branches are in flight sooner when launching eagerly
+            pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
+            pitch, pitchf = pitch.unsqueeze(0), pitchf.unsqueeze(0)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            if not capturing:
+                audio_pad.record_stream(self._side)
+            self._prefetched = (audio_pad, f, f_raw, ev)
+        out = self._vc_dev(model, net_g, sid, audio_pad, pitch, pitchf, times, index, big_npy, index_rate, version, protect)
+        out = out[self.t_pad_tgt: -self.t_pad_tgt].contiguous()
+        out = engine.post_mix(out, tgt_sr, a16, rms_mix_rate)
+        return engine.f32_to_i16(out) if as_int16 else out
+
+    def _pipeline_single_dev(self, model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
+                             rms_mix_rate, version, protect, as_int16=False):
+        """One-chunk utterance with NO host round trip between the input copy and the result copy: high-pass filtfilt
+        (pipeline.py:221), reflect padding (:241), RMVPE, f0 post-processing (rvc/f0/gen.py:10-41), HuBERT + retrieval on a
+        side stream, synthesizer, RMS mix + scaling (:349-360) and the int16 cast (modules.py:181) all run on the device.
+        The second time the same (length, settings) comes in, the ~490 launches are captured into a CUDA graph and replayed
+        from then on (RVCB_GRAPHS=0 turns that off).  Returns a device tensor (float32 in the int16 range, or int16)."""
+        t0 = time()
+        host_ok = getattr(net_g, "accepts_host_scalars", False)
+        sid_t = torch.tensor(sid).unsqueeze(0).long() if host_ok else torch.tensor(sid, device=self.device).unsqueeze(0).long()
+        args = (model, net_g, sid_t, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version, protect, as_int16)
+        x = self._stage_h2d(audio)
+        key = None
+        if host_ok and os.environ.get("RVCB_GRAPHS", "1") != "0" and (index is None or isinstance(index, engine.Index)):
+            key = (int(audio.shape[0]), id(model), id(net_g), int(sid), float(f0_up_key), id(index), float(index_rate), int(if_f0),
+                   int(tgt_sr), float(rms_mix_rate), str(version), float(protect), bool(as_int16))
+        ent = self._graphs.get(key) if key is not None else None
+        if key is None or ent is None:
+            if key is not None:
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = {}
+            out = self._dev_body(x, *args)
+        else:
+            if "graph" not in ent:                      # second sighting: capture (arenas and kernels are warm from the first run)
+                ent["x"] = torch.empty_like(x)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["out"] = self._dev_body(ent["x"], *args)
+                ent["graph"] = g
+            ent["x"].copy_(x, non_blocking=True)
+            ent["graph"].replay()
+            out = ent["out"]
+            times[2] += time() - t0          # launch time only: the replay is asynchronous like the eager path
+        return out
+
     def pipeline(self, model, net_g, sid, audio, times, f0_up_key, f0_method, file_index, index_rate, if_f0, filter_radius, tgt_sr,
                  resample_sr, rms_mix_rate, version, protect, f0_file=None):
         index = big_npy = None
@@ -164,7 +244,14 @@ class Pipeline(object):
             except Exception:
                 traceback.print_exc()
                 index = big_npy = None
-        audio = signal.filtfilt(bh, ah, audio)
+        single = audio.shape[0] + 2 * (self.window // 2) <= self.t_max          # pipeline.py:224: no silence-point chunking
+        if (single and if_f0 in (0, 1) and (if_f0 == 0 or f0_method == "rmvpe") and not hasattr(f0_file, "name")
+                and not (tgt_sr != resample_sr >= 16000) and not getattr(self, "_force_host", False)):
+            as_i16 = getattr(self, "_want_int16", False)
+            out = self._pipeline_single_dev(model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
+                                            rms_mix_rate, version, protect, as_int16=as_i16)
+            return out.cpu().numpy()
+        audio = engine.host_filtfilt(bh, ah, zi_h, audio)       # == signal.filtfilt(bh, ah, audio), bit for bit
         audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
         opt_ts = []
         if audio_pad.shape[0] > self.t_max:

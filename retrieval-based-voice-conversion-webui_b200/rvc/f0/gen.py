@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from rvc_b200 import f0post
-from rvc_b200.engine import Rmvpe
+from rvc_b200.engine import Rmvpe, f0_post as engine_f0_post
 
 
 def post_process(tf0, f0, f0_up_key, manual_x_pad, f0_mel_min=None, f0_mel_max=None, manual_f0=None):
@@ -46,6 +46,12 @@ class Generator(object):
             p_len = wav.shape[0] // self.window
         f0, _, _ = self._rmvpe().infer(wav, thred)
         return f0post.interpolate_f0(f0post.resize_f0(f0.cpu().numpy().astype(np.float64), p_len))
+
+    def calculate_device(self, wav: torch.Tensor, p_len: int, f0_up_key: float, thred: float = 0.03):
+        """``calculate`` for f0_method "rmvpe" without a manual curve, entirely on the device: RMVPE, then the resize / gap
+        fill / key shift / mel quantisation kernel.  Returns device tensors (pitch int64 [p_len], pitchf float32 [p_len])."""
+        f0, _, _ = self._rmvpe().infer(wav, thred)
+        return engine_f0_post(f0, p_len, f0_up_key)
 
     def calculate(self, x, p_len: Optional[int], f0_up_key: int, f0_method: str, filter_radius, manual_f0=None) -> Tuple[np.ndarray, np.ndarray]:
         if f0_method != "rmvpe":

@@ -28,6 +28,7 @@ class SynthesizerB200:
         version = cpt.get("version", "v1")
         self.encoder_dim = 256 if version == "v1" else 768
         self.use_f0 = cpt.get("f0", 1) == 1
+        self.accepts_host_scalars = True     # phone_lengths / sid may be CPU tensors: reading them then costs no device sync
         self.config = list(cpt["config"])
         self.device = dev
         self._synth = Synth(_fold_weight_norm(cpt["weight"]), self.config, self.encoder_dim, dev.index or 0)

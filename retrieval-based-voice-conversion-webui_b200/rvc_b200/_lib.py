@@ -74,6 +74,11 @@ SIGNATURES = {
     "rvcb_index_destroy": (None, [_P]),
     "rvcb_upsample_protect": (_I, [_P, _P, _I, _I, _P, _I, _F, _P, _P]),
     "rvcb_post_mix": (_I, [_P, _L, _I, _P, _L, _F, _P, _P]),
+    "rvcb_host_filtfilt": (_I, [_P, _P, _P, _I, _P, _I, _L, _P]),
+    "rvcb_sosfiltfilt": (_I, [_P, _P, _I, _I, _P, _L, _P, _P, _P]),
+    "rvcb_reflect_pad": (_I, [_P, _L, _L, _P, _P]),
+    "rvcb_f32_to_i16": (_I, [_P, _L, _P, _P]),
+    "rvcb_f0_post": (_I, [_P, _I, _I, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     "rvcb_rmvpe_create": (_I, [_P, C.POINTER(_P)]),
     "rvcb_rmvpe_num_frames": (_I, [_I]),
     "rvcb_rmvpe_infer": (_I, [_P, _P, _I, _F, _P, _P, _P, C.POINTER(_I), _P]),

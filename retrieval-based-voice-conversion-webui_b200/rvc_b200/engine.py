@@ -176,6 +176,76 @@ def post_mix(wav: torch.Tensor, tgt_sr: int, audio16k: torch.Tensor, rms_mix_rat
     return wav
 
 
+def host_filtfilt(b: np.ndarray, a: np.ndarray, zi: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """scipy.signal.filtfilt(b, a, x) (defaults) on the host, in C (rvcb_host_filtfilt); float32 / float64 in, float64 out."""
+    b = np.ascontiguousarray(b, dtype=np.float64); a = np.ascontiguousarray(a, dtype=np.float64)
+    zi = np.ascontiguousarray(zi, dtype=np.float64)
+    x = np.asarray(x).reshape(-1)
+    is32 = x.dtype == np.float32
+    x = np.ascontiguousarray(x, dtype=np.float32 if is32 else np.float64)
+    y = np.empty(x.shape[0], dtype=np.float64)
+    _lib.check(_lib.lib().rvcb_host_filtfilt(b.ctypes.data, a.ctypes.data, zi.ctypes.data, int(b.shape[0]), x.ctypes.data, int(is32),
+                                             int(x.shape[0]), y.ctypes.data))
+    return y
+
+
+def highpass_sos_from_ba(b: np.ndarray, a: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Second-order sections of an odd-order Butterworth high-pass given in (b, a) form, for the device filter: the zeros are
+    the N-fold zero at z = 1 (known exactly; root finding would smear it by eps^(1/N)), the poles are the roots of ``a``
+    polished by Newton steps in extended precision.  Returns (sos [ns,6], zi [ns,2]) with zi = scipy.signal.sosfilt_zi(sos)."""
+    from scipy import signal
+    order = len(a) - 1
+    al = np.array(a, dtype=np.longdouble)
+    r = np.roots(a).astype(np.clongdouble)
+    for _ in range(50):
+        r = r - np.polyval(al, r) / np.polyval(np.polyder(al), r)
+    r = np.array(r, dtype=np.complex128)
+    cplx = sorted([z for z in r if z.imag > 1e-9], key=abs)
+    real = [z.real for z in r if abs(z.imag) <= 1e-9]
+    if 2 * len(cplx) + len(real) != order or len(real) > 1:
+        raise ValueError("unexpected pole pattern")
+    sos = [[1.0, -2.0, 1.0, 1.0, -2.0 * z.real, abs(z) ** 2] for z in cplx] + [[1.0, -1.0, 0.0, 1.0, -p, 0.0] for p in real]
+    sos = np.array(sos, dtype=np.float64)
+    sos[0, :3] *= b[0]
+    return sos, np.ascontiguousarray(signal.sosfilt_zi(sos), dtype=np.float64)
+
+
+def sosfiltfilt(sos: np.ndarray, zi: np.ndarray, edge: int, x: torch.Tensor) -> torch.Tensor:
+    """Device forward-backward IIR over second-order sections (float64 arithmetic): x f32[n] on the device -> f32[n]."""
+    sos = np.ascontiguousarray(sos, dtype=np.float64); zi = np.ascontiguousarray(zi, dtype=np.float64)
+    x = _chk_dev(x.reshape(-1), torch.float32, "x")
+    y = torch.empty_like(x)
+    scratch = torch.empty(x.numel() + 2 * edge + 8, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.lib().rvcb_sosfiltfilt(sos.ctypes.data, zi.ctypes.data, int(sos.shape[0]), int(edge), _p(x), x.numel(), _p(y),
+                                           _p(scratch), _stream_ptr()))
+    return y
+
+
+def reflect_pad(x: torch.Tensor, pad: int) -> torch.Tensor:
+    x = _chk_dev(x.reshape(-1), torch.float32, "x")
+    out = torch.empty(x.numel() + 2 * pad, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().rvcb_reflect_pad(_p(x), x.numel(), int(pad), _p(out), _stream_ptr()))
+    return out
+
+
+def f32_to_i16(x: torch.Tensor) -> torch.Tensor:
+    x = _chk_dev(x.reshape(-1), torch.float32, "x")
+    out = torch.empty(x.numel(), device=x.device, dtype=torch.int16)
+    _lib.check(_lib.lib().rvcb_f32_to_i16(_p(x), x.numel(), _p(out), _stream_ptr()))
+    return out
+
+
+def f0_post(f0: torch.Tensor, p_len: int, f0_up_key: float, f0_min: float = 50.0, f0_max: float = 1100.0):
+    """Device-resident resize + gap fill + key shift + mel quantisation: (pitch i64[p_len], pitchf f32[p_len])."""
+    f0 = _chk_dev(f0.reshape(-1), torch.float32, "f0")
+    pitch = torch.empty(p_len, device=f0.device, dtype=torch.int64)
+    pitchf = torch.empty(p_len, device=f0.device, dtype=torch.float32)
+    scratch = torch.empty(p_len, device=f0.device, dtype=torch.float64)
+    _lib.check(_lib.lib().rvcb_f0_post(_p(f0), f0.numel(), int(p_len), float(pow(2, f0_up_key / 12)), float(f0_min), float(f0_max),
+                                      _p(pitch), _p(pitchf), _p(scratch), _stream_ptr()))
+    return pitch, pitchf
+
+
 class Rmvpe:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0):
         _lib.init(device)

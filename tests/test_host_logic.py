@@ -115,3 +115,20 @@ def test_world_size_2_sharding_and_index_broadcast_gloo():
     assert s0 == s1 and n0 == n1 == 400                     # identical index on both ranks
     assert sorted(m0 + m1) == list(range(11)) and not set(m0) & set(m1)   # every utterance exactly once
     assert t0 == t1 == 11.0
+
+
+def test_host_filtfilt_is_scipy_bit_for_bit():
+    """rvcb_host_filtfilt (C, host) == scipy.signal.filtfilt(bh, ah, x) of pipeline.py:23,221, including the error on inputs
+    no longer than padlen."""
+    from scipy import signal
+    from rvc_b200 import engine
+    bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
+    zi = signal.lfilter_zi(bh, ah)
+    rng = np.random.default_rng(3)
+    for n in (19, 20, 1000, 160000):
+        x = (rng.standard_normal(n) * 0.3).astype(np.float32)
+        assert np.array_equal(signal.filtfilt(bh, ah, x), engine.host_filtfilt(bh, ah, zi, x)), n      # float32 audio (the reference's)
+        x64 = x.astype(np.float64) * 1.0000001
+        assert np.array_equal(signal.filtfilt(bh, ah, x64), engine.host_filtfilt(bh, ah, zi, x64)), n
+    with pytest.raises(RuntimeError, match="padlen"):
+        engine.host_filtfilt(bh, ah, zi, np.zeros(18))

@@ -88,6 +88,12 @@ def test_vc_facade_and_realtime_engine_run():
     assert y.shape == (21 * 480,) and torch.isfinite(y).all()
     y2 = rt.infer(win, 2560, 250, 21, "rmvpe", protect=0.33)
     assert y2.shape == (10080,)
+    # same shapes and settings again: capture into a CUDA graph, then replay; the pitch cache keeps rolling inside the graph
+    cp0 = rt.cache_pitchf.clone()
+    ys = [rt.infer(torch.roll(win, -2560 * i), 2560, 250, 21, "rmvpe") for i in range(1, 4)]
+    assert any("graph" in e for e in rt._graphs.values())
+    assert all(y.shape == (10080,) and torch.isfinite(y).all() and y.abs().max() > 1e-3 for y in ys)
+    assert not torch.equal(ys[1], ys[2]) and not torch.equal(cp0, rt.cache_pitchf)
 
 
 @pytest.mark.parametrize("rate", [0.25, 1.0])
@@ -189,3 +195,76 @@ def test_no_f0_model_through_the_facade_and_realtime_engine():
     win = torch.from_numpy(OW.synth_voice(2.72, seed=9).numpy()[:43520]).cuda()
     y = rt.infer(win, 2560, 250, 21, "rmvpe")
     assert y.shape == (21 * 480,) and torch.isfinite(y).all()
+
+
+def test_device_front_end_kernels_match_host_dsp():
+    """filtfilt (float64, block-parallel IIR), reflect padding, f0 post-processing and the int16 cast on the device vs
+    scipy / numpy / the oracle's f0 post-processing."""
+    from scipy import signal
+    from rvc_b200 import engine
+    from oracle import rmvpe as ORM
+    bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
+    sos, zi = engine.highpass_sos_from_ba(bh, ah)
+    rng = np.random.default_rng(5)
+    for n in (19, 4000, 160000, 700001):
+        x = (rng.standard_normal(n) * 0.3 + 0.05).astype(np.float32)
+        if n == 4000:
+            x += (0.4 * np.sin(2 * np.pi * 30 * np.arange(n) / 16000)).astype(np.float32)       # energy below the 48 Hz corner
+        ref = signal.filtfilt(bh, ah, x)                      # the reference's direct-form filter (pipeline.py:221)
+        got = engine.sosfiltfilt(sos, zi, 18, torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.abs(got - ref).max() <= 2e-7, (n, np.abs(got - ref).max())     # float32 output: half an ulp at |y| ~ 1 is 6e-8
+    x = torch.from_numpy(rng.standard_normal(5000).astype(np.float32))
+    assert np.array_equal(engine.reflect_pad(x.cuda(), 48).cpu().numpy(), np.pad(x.numpy(), (48, 48), mode="reflect"))
+    w = (rng.standard_normal(100000) * 20000).astype(np.float32)
+    assert np.array_equal(engine.f32_to_i16(torch.from_numpy(w).cuda()).cpu().numpy(), w.astype(np.int16))
+    # f0 contours with leading / interior / trailing unvoiced runs, isolated frames, all-unvoiced, resize up and down
+    cases = []
+    f0 = (200 + 50 * np.sin(np.arange(1601) / 40.0)).astype(np.float32)
+    f0[:30] = 0; f0[100:160] = 0; f0[700:701] = 0; f0[1500:] = 0; f0[rng.random(1601) < 0.05] = 0
+    cases += [(f0, 1600, 0), (f0, 1601, 5), (f0, 2000, -7), (f0[:300], 157, 12), (np.zeros(50, np.float32), 49, 3)]
+    g = (80 + 900 * rng.random(400)).astype(np.float32); g[rng.random(400) < 0.5] = 0
+    cases += [(g, 399, 0), (g, 400, 24), (g[-1:], 1, 0)]
+    for f0, p_len, key in cases:
+        want_c, want_f = ORM.post_process(ORM.interpolate_f0(ORM.resize_f0(f0.astype(np.float64), p_len)), key)
+        pitch, pitchf = engine.f0_post(torch.from_numpy(f0).cuda(), p_len, key)
+        assert np.array_equal(pitch.cpu().numpy(), want_c.astype(np.int64)), (p_len, key)
+        assert np.array_equal(pitchf.cpu().numpy(), want_f.astype(np.float32)), (p_len, key)
+
+
+def test_device_resident_utterance_path_equals_host_path():
+    """vc_single through the device-resident single-chunk path (no host round trip) vs the host-DSP path of the same
+    drop-in, same torch seed -> same noise draws: identical int16 audio up to 2 LSB."""
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.5, 1200)
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    vc.get_vc(OW.synth_cpt(1234, "v2"))
+    gidx = Index.from_oracle_layout(idx)
+    outs = []
+    for force_host in (False, True):
+        vc.pipeline._force_host = force_host
+        torch.manual_seed(11); torch.cuda.manual_seed(11)
+        info, (sr, wav) = vc.vc_single(0, audio, 2, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+        assert info.startswith("Success"), info
+        outs.append(wav.astype(np.int32))
+    assert outs[0].shape == outs[1].shape
+    # not bit for bit: the device filter is a second-order-section cascade (~4e-8 from scipy's direct form), and one float32 ulp
+    # at the input moves fp16 operand roundings downstream and the global peak-normalisation factor
+    a, b = outs[0].astype(np.float64), outs[1].astype(np.float64)
+    assert np.sqrt(np.mean((a - b) ** 2)) <= 0.01 * np.sqrt(np.mean(b ** 2)), np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))
+    # third and fourth call with the same settings: CUDA-graph capture, then replay; fresh noise every call, same envelope
+    vc.pipeline._force_host = False
+    reps = []
+    for _ in range(3):
+        info, (sr, wav) = vc.vc_single(0, audio, 2, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+        assert info.startswith("Success"), info
+        reps.append(wav.astype(np.float64))
+    assert any("graph" in e for e in vc.pipeline._graphs.values())
+    assert not np.array_equal(reps[1], reps[2])                      # the captured randn draws advance on every replay
+    for r in reps:
+        assert r.shape == b.shape and np.abs(r).max() > 1000
+        assert abs(np.sqrt(np.mean(r ** 2)) / np.sqrt(np.mean(b ** 2)) - 1) < 0.05
