@@ -299,7 +299,7 @@ def main():
         # in this unfused layer-by-layer design: algorithmic bytes = activations in + weights + fp32 residual in + outputs
         "roofline": {"bound": "hbm", "achieved": ws_bytes / (ws_ms * 1e-3) / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                      "frac": ws_bytes / (ws_ms * 1e-3) / 1e9 / pk.get("hbm_gbs"),
-                     "traffic": 251.2e6, "traffic_note": "dram read+write of one stage-2 c2 launch (ncu --set full, profiles/prof_r1e_ws_metrics.txt) vs 294 MB algorithmic",
+                     "traffic": 244.0e6, "traffic_note": "dram read+write of one stage-2 c2 launch (ncu --set full, profiles/prof_r1u_ws2_metrics.txt: 147.4 MB read + 96.6 MB written, 47.2 us) vs 294 MB algorithmic; part of the fp16/fp32 output is still in L2 when the kernel ends",
                      "kernel": "gemm_ws_kernel<*> (vocoder resblock convolutions, stages 1-3 + conv_post)", "launches_per_step": ws_n,
                      "avg_launch_us": ws_ms / max(ws_n, 1) * 1e3, "algorithmic_bytes_per_step": ws_bytes, "peak_source": pk_src,
                      "tensor_view": {"achieved_tflops": ws_flops / (ws_ms * 1e-3) / 1e12, "frac_of_bf16_sustained": ws_flops / (ws_ms * 1e-3) / 1e12 / peak}},

@@ -96,9 +96,9 @@ int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio1
 int rvcb_host_filtfilt(const double* b, const double* a, const double* zi, int ncoef, const void* x, int x_is_f32, int64_t n, double* y);
 /* The same filter on the DEVICE, as a cascade of second-order sections (scipy.signal.sosfiltfilt semantics with padtype "odd",
  * padlen = edge): sos f64[n_sections,6] rows [b0 b1 b2 1 a1 a2], zi f64[n_sections,2] = scipy.signal.sosfilt_zi(sos) (edge state
- * per unit input level).  d_x f32[n] -> d_y f32[n], float64 arithmetic.  The recurrence is cut into 256 blocks per section
- * (zero-state pass, 2x2 state propagation A^L, exact re-run), so it agrees with the host filter to ~1e-7, not bit for bit: the
- * direct 5th-order form cannot be block-propagated in float64.  d_scratch: >= n + 2*edge doubles. */
+ * per unit input level).  d_x f32[n] -> d_y f32[n], float64 arithmetic.  The recurrence is cut into 1024 blocks per section
+ * (zero-state pass, log-step 2x2 state prefix with A^L, exact re-run), so it agrees with the host filter to ~1e-7, not bit for
+ * bit: the direct 5th-order form cannot be block-propagated in float64.  d_scratch: >= n + 2*edge + 4120 doubles. */
 int rvcb_sosfiltfilt(const double* sos, const double* zi, int n_sections, int edge, const float* d_x, int64_t n, float* d_y,
                      double* d_scratch, void* stream);
 /* np.pad(x, (pad, pad), mode="reflect") on the device (pipeline.py:241): d_out f32[n + 2*pad], pad < n */
@@ -110,7 +110,7 @@ int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream);
  * replaces: F0Predictor._resize_f0 + _interpolate_f0 (rvc/f0/f0.py:31-78) and post_process (rvc/f0/gen.py:10-41, without
  * a manual f0 curve), float64 with numpy's operation order.  d_f0 f32[n_frames] (Hz, 0 = unvoiced) -> d_pitch i64[p_len]
  * (coarse mel bins 1..255) and d_pitchf f32[p_len] (Hz, gaps filled, shifted by key_factor = 2^(f0_up_key/12)).
- * d_scratch: >= p_len doubles. */
+ * d_scratch: >= 2 * p_len doubles. */
 int rvcb_f0_post(const float* d_f0, int n_frames, int p_len, double key_factor, double f0_min, double f0_max, int64_t* d_pitch,
                  float* d_pitchf, double* d_scratch, void* stream);
 

@@ -178,8 +178,77 @@ __global__ void softmax_kernel(const float* __restrict__ S, long lds, int T, __h
     }
 }
 
+// Rows of up to 1024 scores: one WARP per row, the row lives in registers (32 values per lane), reductions are shuffles only --
+// no shared memory, no block barrier (the block-per-row kernel above spends its time in 5 __syncthreads per 800-element row).
+__global__ void __launch_bounds__(256) softmax_warp_kernel(const float* __restrict__ S, long lds, int T, long n_rows, __half* __restrict__ P,
+                                                           long ldp, const float* __restrict__ qrel, long ldq, int win,
+                                                           __half* __restrict__ prel) {
+    pdl_trigger();
+    const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(r % T);
+    const float* sr = S + r * lds;
+    float v[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int j = q * 32 + lane;
+        float x = -INFINITY;
+        if (j < T) {
+            x = sr[j];
+            if (qrel) {
+                const int d = j - i;
+                if (d >= -win && d <= win) x += qrel[r * ldq + d + win];
+            }
+        }
+        v[q] = x;
+        mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const float e = (q * 32 + lane < T) ? expf(v[q] - mx) : 0.f;
+        v[q] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    __half* pr = P + r * ldp;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const int j = q * 32 + lane;
+        if (j < ldp) pr[j] = __float2half_rn(v[q] * inv);      // columns T..ldp-1 are written as zeros (v == 0 there)
+    }
+    if (prel) {
+        // band of +-win around the diagonal, gathered from the lanes that hold those columns
+#pragma unroll
+        for (int half_ = 0; half_ < 2; ++half_) {
+            const int qq = lane + 32 * half_;                   // output slot 0..63
+            const int j = i + qq - win;
+            float pv = 0.f;
+            // every lane must take part in the shuffles: loop over the (at most 3) register rows the band can touch
+            const int jc = min(max(j, 0), T - 1);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const float got = __shfl_sync(0xffffffffu, v[q], jc & 31);
+                if ((jc >> 5) == q) pv = got;
+            }
+            prel[r * 64 + qq] = __float2half_rn((qq <= 2 * win && j >= 0 && j < T) ? pv * inv : 0.f);
+        }
+    }
+}
+
 void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, const float* qrel, long ldq, int win, __half* prel,
                   cudaStream_t s) {
+    if (T <= 1024 && ldp <= 1024) {
+        const long rows = (long)H * T;
+        softmax_warp_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, s>>>(S, lds, T, rows, P, ldp, qrel, ldq, win, prel);
+        KERNEL_CHECK();
+        count_launch();
+        return;
+    }
     RVCB_CHECK((size_t)T * 4 <= 48 * 1024, "softmax: row too long");
     softmax_kernel<<<H * T, 256, T * sizeof(float), s>>>(S, lds, T, P, ldp, qrel, ldq, win, prel);
     KERNEL_CHECK();
@@ -624,101 +693,164 @@ void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long
 // ------------------------------------------------------------------------------------------------
 // input / output plumbing kernels
 // ------------------------------------------------------------------------------------------------
-// Forward-backward IIR (scipy filtfilt semantics: odd extension by `edge` samples, steady-state edge conditions) on ONE CTA,
-// as a cascade of second-order sections.  The 5th-order direct form of the reference has poles clustered at |z| = 0.98..0.994;
-// its 5x5 state matrix is too non-normal to propagate across blocks in float64 (A^L computed to ~1e13 instead of ~1), the 2x2
-// section matrices are benign (|A^L| <= ~30).  Per section and direction, each of the 256 threads owns a block of L samples:
-//   pass 1  zero-state run over the block -> its end state                      (parallel)
-//   scan    true start state of every block: s <- A^L s + end_state             (thread 0; A^L by repeated squaring)
-//   pass 2  exact re-run of the block from its start state, writing y in place  (parallel)
+// Forward-backward IIR (scipy filtfilt semantics: odd extension by `edge` samples, steady-state edge conditions) as a cascade
+// of second-order sections, float64.  The 5th-order direct form of the reference has poles clustered at |z| = 0.98..0.994; its
+// 5x5 state matrix is too non-normal to propagate across blocks in float64 (A^L comes out ~1e13 instead of ~1), the 2x2 section
+// matrices are benign (|A^L| <= ~30).  The recurrence is cut into IIR_NB blocks of L samples, one thread each, spread over
+// many SMs (FP64 issue rate per SM is what bounds a one-CTA version: 1.1 ms measured).  Per direction and section:
+//   zero-state end state of every block                         (sos_sweep_kernel, fused with the previous section's re-run)
+//   start state of every block: s_k = sum_{j<=k} M^(k-j) u_j     (sos_scan_kernel: log-step prefix over IIR_NB blocks, M = A^L)
+//   exact re-run of every block from its start state, in place   (sos_sweep_kernel)
 // DF2T section: y = z0 + b0 x;  z0' = z1 + b1 x - a1 y;  z1' = b2 x - a2 y;   A = [[-a1, 1], [-a2, 0]].
-constexpr int IIR_T = 512, IIR_B = 16;      // threads (= blocks of the recurrence), samples fetched per batch
+constexpr int IIR_NB = 1024, IIR_B = 16, IIR_LOG = 10;
+struct SosSec { double q[6]; };
+struct SosScanP { double zi[2]; double mp[IIR_LOG][4]; };      // edge state per unit input, and M^(2^d), d = 0..9
 __device__ __forceinline__ double sos_step(double& z0, double& z1, const double* c, double x) {
     const double y = z0 + c[0] * x;
     z0 = z1 + c[1] * x - c[4] * y;
     z1 = c[2] * x - c[5] * y;
     return y;
 }
-__global__ void __launch_bounds__(IIR_T) sosfiltfilt_kernel(const SosCoef c, const float* __restrict__ x, long n, int edge,
-                                                            float* __restrict__ out, double* __restrict__ w) {
-    __shared__ double s_st[IIR_T][2];      // zero-state end state of each block, then its true start state
-    const long m = n + 2L * edge;
-    const long L = (m + IIR_T - 1) / IIR_T;
-    const int t = threadIdx.x;
-    const long lo = (long)t * L, hi = min(lo + L, m);
-    auto ext = [&](long i) -> double {     // odd extension, formed in float32 like numpy does on float32 audio
-        if (i < edge) return (double)__fsub_rn(2.0f * x[0], x[edge - i]);
-        if (i < edge + n) return (double)x[i - edge];
-        return (double)__fsub_rn(2.0f * x[n - 1], x[n - 2 - (i - edge - n)]);
-    };
-    __shared__ double x0s;                 // first sample of the cascade's input in this direction (edge condition)
-    for (int dir = 0; dir < 2; ++dir) {
-        if (t == 0) x0s = (dir == 0) ? ext(0) : w[m - 1];
-        __syncthreads();
-        for (int sec = 0; sec < c.ns; ++sec) {
-            const double* q = c.sos[sec];
-            const bool first = (dir == 0 && sec == 0);
-            auto in = [&](long i) -> double { return first ? ext(i) : w[dir == 0 ? i : m - 1 - i]; };
-            {   // pass 1 (samples are fetched IIR_B at a time so their load latencies overlap; the recurrence then runs from registers)
-                double z0 = 0.0, z1 = 0.0;
-                if (hi - lo == L) {
-                    for (long i0 = lo; i0 < hi; i0 += IIR_B) {
-                        double v[IIR_B];
+// w = odd extension of x (formed in float32 like numpy does on float32 audio, then widened)
+__global__ void sos_extend_kernel(const float* __restrict__ x, long n, int edge, double* __restrict__ w) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + 2L * edge) return;
+    float v;
+    if (i < edge) v = __fsub_rn(2.0f * x[0], x[edge - i]);
+    else if (i < edge + n) v = x[i - edge];
+    else v = __fsub_rn(2.0f * x[n - 1], x[n - 2 - (i - edge - n)]);
+    w[i] = (double)v;
+}
+// One thread per recurrence block.  has_run: re-run section `run` exactly from start[] (in place); has_zs: zero-state pass of
+// section `zs` over the block's (new) values -> ends[].  Both in one sweep when a section hands over to the next one.
+__global__ void __launch_bounds__(32) sos_sweep_kernel(double* __restrict__ w, long m, long L, int dir, int has_run, SosSec run,
+                                                       const double* __restrict__ start, int has_zs, SosSec zs,
+                                                       double* __restrict__ ends) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= IIR_NB) return;
+    const long lo = min((long)t * L, m), hi = min(lo + L, m);
+    const long cnt = hi - lo;
+    double* p = w + (dir == 0 ? lo : m - 1 - lo);          // element j of the block in processing order is p[j * sg]
+    const long sg = dir == 0 ? 1 : -1;
+    double r0 = 0.0, r1 = 0.0, z0 = 0.0, z1 = 0.0;
+    if (has_run) { r0 = start[2 * t]; r1 = start[2 * t + 1]; }
+    long j = 0;
+    for (; j + IIR_B <= cnt; j += IIR_B) {
+        double v[IIR_B];
 #pragma unroll
-                        for (int k = 0; k < IIR_B; ++k) v[k] = (i0 + k < hi) ? in(i0 + k) : 0.0;
+        for (int k = 0; k < IIR_B; ++k) v[k] = p[(j + k) * sg];
+        if (has_run) {
 #pragma unroll
-                        for (int k = 0; k < IIR_B; ++k)
-                            if (i0 + k < hi) sos_step(z0, z1, q, v[k]);
-                    }
-                }
-                s_st[t][0] = z0; s_st[t][1] = z1;
+            for (int k = 0; k < IIR_B; ++k) {
+                v[k] = sos_step(r0, r1, run.q, v[k]);
+                p[(j + k) * sg] = v[k];
             }
-            __syncthreads();
-            if (t == 0) {
-                double p00 = -q[4], p01 = 1.0, p10 = -q[5], p11 = 0.0;      // P = A
-                double r00 = 1.0, r01 = 0.0, r10 = 0.0, r11 = 1.0;          // R = I
-                for (long e = L; e > 0; e >>= 1) {
-                    if (e & 1) {
-                        const double a = r00 * p00 + r01 * p10, b = r00 * p01 + r01 * p11;
-                        const double cc = r10 * p00 + r11 * p10, d = r10 * p01 + r11 * p11;
-                        r00 = a; r01 = b; r10 = cc; r11 = d;
-                    }
-                    const double a = p00 * p00 + p01 * p10, b = p00 * p01 + p01 * p11;
-                    const double cc = p10 * p00 + p11 * p10, d = p10 * p01 + p11 * p11;
-                    p00 = a; p01 = b; p10 = cc; p11 = d;
-                }
-                // edge condition: the cascade has been fed its first input sample forever (sosfilt_zi is per unit input level)
-                double s0 = c.zi[sec][0] * x0s, s1 = c.zi[sec][1] * x0s;
-                for (int bq = 0; bq < IIR_T; ++bq) {
-                    const double n0 = r00 * s0 + r01 * s1 + s_st[bq][0];
-                    const double n1 = r10 * s0 + r11 * s1 + s_st[bq][1];
-                    s_st[bq][0] = s0; s_st[bq][1] = s1;
-                    s0 = n0; s1 = n1;
-                }
-            }
-            __syncthreads();
-            {   // pass 2: every thread reads and writes only its own block (in place from the second pass on)
-                double z0 = s_st[t][0], z1 = s_st[t][1];
-                for (long i0 = lo; i0 < hi; i0 += IIR_B) {
-                    double v[IIR_B];
+        }
+        if (has_zs) {
 #pragma unroll
-                    for (int k = 0; k < IIR_B; ++k) v[k] = (i0 + k < hi) ? in(i0 + k) : 0.0;
-#pragma unroll
-                    for (int k = 0; k < IIR_B; ++k)
-                        if (i0 + k < hi) w[dir == 0 ? i0 + k : m - 1 - (i0 + k)] = sos_step(z0, z1, q, v[k]);
-                }
-            }
-            __syncthreads();
+            for (int k = 0; k < IIR_B; ++k) sos_step(z0, z1, zs.q, v[k]);
         }
     }
-    for (long i = t; i < n; i += IIR_T) out[i] = (float)w[edge + i];
+    for (; j < cnt; ++j) {
+        double v = p[j * sg];
+        if (has_run) { v = sos_step(r0, r1, run.q, v); p[j * sg] = v; }
+        if (has_zs) sos_step(z0, z1, zs.q, v);
+    }
+    if (has_zs) {
+        const bool full = (cnt == L);                       // only a full block's end state feeds a later block
+        ends[2 * t] = full ? z0 : 0.0;
+        ends[2 * t + 1] = full ? z1 : 0.0;
+    }
+}
+// start[k] = sum_{j<=k} M^(k-j) u_j with u_0 = zi * x0 (edge condition: the cascade has been fed its first input sample forever;
+// x0 = w[x0_idx] read BEFORE the section's sweeps overwrite it -- it is stored in x0_keep by the first scan of a direction)
+__global__ void __launch_bounds__(IIR_NB) sos_scan_kernel(const double* __restrict__ ends, double* __restrict__ start, SosScanP sp,
+                                                          const double* __restrict__ w, long x0_idx, double* __restrict__ x0_keep,
+                                                          int first_of_dir) {
+    __shared__ double u[2][IIR_NB][2];
+    const int t = threadIdx.x;
+    double x0;
+    if (first_of_dir) {
+        x0 = w[x0_idx];
+        if (t == 0) *x0_keep = x0;
+    } else {
+        x0 = *x0_keep;
+    }
+    double a0 = t == 0 ? sp.zi[0] * x0 : ends[2 * (t - 1)];
+    double a1 = t == 0 ? sp.zi[1] * x0 : ends[2 * (t - 1) + 1];
+    int cur = 0;
+    u[0][t][0] = a0; u[0][t][1] = a1;
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < IIR_LOG; ++d) {
+        const int off = 1 << d;
+        if (t >= off) {
+            const double b0 = u[cur][t - off][0], b1 = u[cur][t - off][1];
+            a0 += sp.mp[d][0] * b0 + sp.mp[d][1] * b1;
+            a1 += sp.mp[d][2] * b0 + sp.mp[d][3] * b1;
+        }
+        cur ^= 1;
+        u[cur][t][0] = a0; u[cur][t][1] = a1;
+        __syncthreads();
+    }
+    start[2 * t] = a0;
+    start[2 * t + 1] = a1;
+}
+__global__ void sos_finish_kernel(const double* __restrict__ w, long n, int edge, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)w[edge + i];
 }
 void sosfiltfilt(const SosCoef& c, const float* x, long n, int edge, float* y, double* scratch, cudaStream_t s) {
     RVCB_CHECK(c.ns >= 1 && c.ns <= 4 && edge >= 0, "sosfiltfilt: 1..4 sections");
     RVCB_CHECK(n > edge, "The length of the input vector x must be greater than padlen");
-    sosfiltfilt_kernel<<<1, IIR_T, 0, s>>>(c, x, n, edge, y, scratch);
+    const long m = n + 2L * edge;
+    const long L = (m + IIR_NB - 1) / IIR_NB;
+    double* w = scratch;
+    double* ends = scratch + ((m + 7) & ~7L);
+    double* start = ends + 2 * IIR_NB;
+    double* x0_keep = start + 2 * IIR_NB;
+    SosSec sec[4];
+    SosScanP sp[4];
+    for (int k = 0; k < c.ns; ++k) {
+        for (int i = 0; i < 6; ++i) sec[k].q[i] = c.sos[k][i];
+        sp[k].zi[0] = c.zi[k][0]; sp[k].zi[1] = c.zi[k][1];
+        // M = A^L by repeated squaring, then its 2^d powers
+        double P[4] = {-c.sos[k][4], 1.0, -c.sos[k][5], 0.0}, R[4] = {1.0, 0.0, 0.0, 1.0};
+        auto mul = [](const double* a, const double* b, double* o) {
+            const double t0 = a[0] * b[0] + a[1] * b[2], t1 = a[0] * b[1] + a[1] * b[3];
+            const double t2 = a[2] * b[0] + a[3] * b[2], t3 = a[2] * b[1] + a[3] * b[3];
+            o[0] = t0; o[1] = t1; o[2] = t2; o[3] = t3;
+        };
+        for (long e = L; e > 0; e >>= 1) {
+            if (e & 1) mul(R, P, R);
+            mul(P, P, P);
+        }
+        for (int d = 0; d < IIR_LOG; ++d) {
+            for (int i = 0; i < 4; ++i) sp[k].mp[d][i] = R[i];
+            mul(R, R, R);
+        }
+    }
+    sos_extend_kernel<<<(unsigned)ceil_div_l(m, 256), 256, 0, s>>>(x, n, edge, w);
     KERNEL_CHECK();
-    count_launch();
+    int launches = 1;
+    const unsigned gsw = IIR_NB / 32;
+    for (int dir = 0; dir < 2; ++dir) {
+        // zero-state pass of section 0, then per section: scan -> exact re-run (fused with the next section's zero-state pass)
+        sos_sweep_kernel<<<gsw, 32, 0, s>>>(w, m, L, dir, 0, sec[0], start, 1, sec[0], ends);
+        KERNEL_CHECK();
+        ++launches;
+        for (int k = 0; k < c.ns; ++k) {
+            sos_scan_kernel<<<1, IIR_NB, 0, s>>>(ends, start, sp[k], w, dir == 0 ? 0 : m - 1, x0_keep, k == 0 ? 1 : 0);
+            KERNEL_CHECK();
+            const int nxt = (k + 1 < c.ns) ? 1 : 0;
+            sos_sweep_kernel<<<gsw, 32, 0, s>>>(w, m, L, dir, 1, sec[k], start, nxt, sec[nxt ? k + 1 : k], ends);
+            KERNEL_CHECK();
+            launches += 2;
+        }
+    }
+    sos_finish_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(w, n, edge, y);
+    KERNEL_CHECK();
+    count_launch(launches + 1);
 }
 
 __global__ void reflect_pad_1d_kernel(const float* __restrict__ x, long n, long pad, float* __restrict__ out) {
@@ -746,12 +878,15 @@ void f32_to_i16(const float* x, long n, short* out, cudaStream_t s) {
 }
 
 // f0 post-processing, one block.  Phase 1 (parallel): resize by np.interp over the NaN-marked contour (compiled_base.c
-// arr_interp: exact-hit shortcut, slope*(x - xp[j]) + fp[j], the two NaN fallbacks), NaN -> 0.  Phase 2 (thread 0): the
-// gap fill of F0Predictor._interpolate_f0 as a run scan.  Phase 3 (parallel): key shift and mel quantisation of
+// arr_interp: exact-hit shortcut, slope*(x - xp[j]) + fp[j], the two NaN fallbacks), NaN -> 0.  Phase 2 (parallel): the
+// gap fill of F0Predictor._interpolate_f0 from nearest-voiced-neighbour indices.  Phase 3 (parallel): key shift and mel quantisation of
 // post_process.  All float64 with explicit round-to-nearest mul/add (no FMA contraction), i.e. numpy's arithmetic.
 __global__ void __launch_bounds__(256) f0_post_kernel(const float* __restrict__ f0, int L, int n, double key_factor, double mel_min,
                                                       double mel_max, long long* __restrict__ pitch, float* __restrict__ pitchf,
-                                                      double* __restrict__ data) {
+                                                      double* __restrict__ gdata, int use_smem) {
+    extern __shared__ double f0_sdata[];
+    double* data = use_smem ? f0_sdata : gdata;        // the gap fill walks this array: keep it on chip when it fits
+    int* nvb = use_smem ? reinterpret_cast<int*>(f0_sdata + n) : reinterpret_cast<int*>(gdata + n);   // next voiced index
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     auto src = [&](int j) -> double {
         const double v = (double)f0[j];
@@ -779,33 +914,55 @@ __global__ void __launch_bounds__(256) f0_post_kernel(const float* __restrict__ 
         data[i] = isnan(r) ? 0.0 : r;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int i = 0;
-        double last_value = 0.0;
-        while (i < n) {
+    {
+        // Gap fill of F0Predictor._interpolate_f0, per element: with pv / nv the nearest voiced frames on either side of an
+        // unvoiced frame i (run = pv+1 .. nv-1),  nv < n-1 and pv >= 0 -> linear ramp  data[pv] + step * (i - pv),
+        // step = (data[nv] - data[pv]) / (nv - pv - 1);  nv < n-1 and no pv -> data[nv];  otherwise (the run reaches the end, or
+        // its right neighbour is the very last frame) -> hold data[pv] (0 if none); in that last case the reference's slice
+        // assignment data[i:n] also overwrites the (voiced) final frame.  No other voiced frame is ever written, so the fill is
+        // done in place; each thread walks one contiguous chunk with carries from a 256-entry summary.
+        __shared__ int s_first[256], s_last[256];
+        const int t = threadIdx.x;
+        const int per = (n + 255) / 256;
+        const int c0 = min(t * per, n), c1 = min(c0 + per, n);
+        int fv = n, lv = -1;
+        for (int i = c0; i < c1; ++i)
             if (data[i] > 0.0) {
-                last_value = data[i];
-                ++i;
+                if (fv == n) fv = i;
+                lv = i;
+            }
+        s_first[t] = fv; s_last[t] = lv;
+        const bool last_overwritten = n >= 2 && data[n - 1] > 0.0 && !(data[n - 2] > 0.0);   // read before anyone writes
+        __syncthreads();
+        int pv = -1, nx = n;
+        for (int k = t - 1; k >= 0; --k)
+            if (s_last[k] >= 0) { pv = s_last[k]; break; }
+        for (int k = t + 1; k < 256; ++k)
+            if (s_first[k] < n) { nx = s_first[k]; break; }
+        for (int i = c1 - 1; i >= c0; --i) {
+            if (data[i] > 0.0) nx = i;
+            else nvb[i] = nx;
+        }
+        for (int i = c0; i < c1; ++i) {
+            if (data[i] > 0.0) {
+                if (i == n - 1 && last_overwritten) data[i] = pv >= 0 ? data[pv] : 0.0;
+                pv = i;
                 continue;
             }
-            int j = i + 1;
-            while (j < n && !(data[j] > 0.0)) ++j;
-            const int jj = j < n ? j : (i + 1 < n ? n - 1 : i + 1);
-            if (jj < n - 1) {
-                if (last_value > 0.0) {
-                    const double base = data[i - 1];
-                    const double step = __ddiv_rn(__dsub_rn(data[jj], base), (double)(jj - i));
-                    for (int k = i; k < jj; ++k) data[k] = __dadd_rn(base, __dmul_rn(step, (double)(k - i + 1)));
+            const int nv = nvb[i];
+            double val;
+            if (nv < n - 1) {
+                if (pv >= 0) {
+                    const double base = data[pv];
+                    const double step = __ddiv_rn(__dsub_rn(data[nv], base), (double)(nv - (pv + 1)));
+                    val = __dadd_rn(base, __dmul_rn(step, (double)(i - pv)));
                 } else {
-                    const double v = data[jj];
-                    for (int k = i; k < jj; ++k) data[k] = v;
+                    val = data[nv];
                 }
-                if (jj > i) last_value = data[jj - 1];
-                i = jj;
             } else {
-                for (int k = i; k < n; ++k) data[k] = last_value;
-                i = n;
+                val = pv >= 0 ? data[pv] : 0.0;
             }
+            data[i] = val;
         }
     }
     __syncthreads();
@@ -824,7 +981,14 @@ void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double
              double* scratch, cudaStream_t s) {
     RVCB_CHECK(n_frames >= 1 && p_len >= 1, "f0_post: empty contour");
     const double mel_min = 1127.0 * std::log(1.0 + f0_min / 700.0), mel_max = 1127.0 * std::log(1.0 + f0_max / 700.0);
-    f0_post_kernel<<<1, 256, 0, s>>>(f0, n_frames, p_len, key_factor, mel_min, mel_max, pitch, pitchf, scratch);
+    const int use_smem = p_len <= 16000 ? 1 : 0;       // 192 KB of the 227 KB a CTA may opt into
+    const size_t smem = use_smem ? (size_t)p_len * 12 : 0;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(f0_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16000 * 12));
+        configured = true;
+    }
+    f0_post_kernel<<<1, 256, smem, s>>>(f0, n_frames, p_len, key_factor, mel_min, mel_max, pitch, pitchf, scratch, use_smem);
     KERNEL_CHECK();
     count_launch();
 }

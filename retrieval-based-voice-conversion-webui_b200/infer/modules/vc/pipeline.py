@@ -182,10 +182,12 @@ class Pipeline(object):
         self._prefetched = None
         if if_f0 == 1:
             cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)                       # the side stream depends on the padded audio only, not on RMVPE
             # f0 first: RMVPE has the fewer launches, so both branches are in flight sooner when launching eagerly
             pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
             pitch, pitchf = pitch.unsqueeze(0), pitchf.unsqueeze(0)
-            self._side.wait_stream(cur)
+            self._side.wait_event(fork)
             with torch.cuda.stream(self._side):
                 f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)
                 ev = torch.cuda.Event()

@@ -215,7 +215,7 @@ def sosfiltfilt(sos: np.ndarray, zi: np.ndarray, edge: int, x: torch.Tensor) -> 
     sos = np.ascontiguousarray(sos, dtype=np.float64); zi = np.ascontiguousarray(zi, dtype=np.float64)
     x = _chk_dev(x.reshape(-1), torch.float32, "x")
     y = torch.empty_like(x)
-    scratch = torch.empty(x.numel() + 2 * edge + 8, device=x.device, dtype=torch.float64)
+    scratch = torch.empty(x.numel() + 2 * edge + 8 + 4 * 1024 + 16, device=x.device, dtype=torch.float64)
     _lib.check(_lib.lib().rvcb_sosfiltfilt(sos.ctypes.data, zi.ctypes.data, int(sos.shape[0]), int(edge), _p(x), x.numel(), _p(y),
                                            _p(scratch), _stream_ptr()))
     return y
@@ -240,7 +240,7 @@ def f0_post(f0: torch.Tensor, p_len: int, f0_up_key: float, f0_min: float = 50.0
     f0 = _chk_dev(f0.reshape(-1), torch.float32, "f0")
     pitch = torch.empty(p_len, device=f0.device, dtype=torch.int64)
     pitchf = torch.empty(p_len, device=f0.device, dtype=torch.float32)
-    scratch = torch.empty(p_len, device=f0.device, dtype=torch.float64)
+    scratch = torch.empty(2 * p_len, device=f0.device, dtype=torch.float64)
     _lib.check(_lib.lib().rvcb_f0_post(_p(f0), f0.numel(), int(p_len), float(pow(2, f0_up_key / 12)), float(f0_min), float(f0_max),
                                       _p(pitch), _p(pitchf), _p(scratch), _stream_ptr()))
     return pitch, pitchf

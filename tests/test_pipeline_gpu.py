@@ -224,6 +224,10 @@ def test_device_front_end_kernels_match_host_dsp():
     cases += [(f0, 1600, 0), (f0, 1601, 5), (f0, 2000, -7), (f0[:300], 157, 12), (np.zeros(50, np.float32), 49, 3)]
     g = (80 + 900 * rng.random(400)).astype(np.float32); g[rng.random(400) < 0.5] = 0
     cases += [(g, 399, 0), (g, 400, 24), (g[-1:], 1, 0)]
+    for _ in range(150):       # short random contours: every run / edge pattern of the gap fill (incl. the overwritten last frame)
+        n = int(rng.integers(1, 40))
+        h = (50 + 500 * rng.random(n)).astype(np.float32); h[rng.random(n) < rng.random()] = 0
+        cases.append((h, n if rng.random() < 0.7 else int(rng.integers(1, 60)), int(rng.integers(-12, 13))))
     for f0, p_len, key in cases:
         want_c, want_f = ORM.post_process(ORM.interpolate_f0(ORM.resize_f0(f0.astype(np.float64), p_len)), key)
         pitch, pitchf = engine.f0_post(torch.from_numpy(f0).cuda(), p_len, key)

@@ -53,3 +53,25 @@ for _ in range(20):
 pr.disable()
 st = pstats.Stats(pr)
 st.sort_stats("cumulative").print_stats(45)
+
+# GPU-side view of the same call: graph replay alone (events on the current stream), then the host-visible pieces
+pipe = vc.pipeline
+ent = next((e for e in pipe._graphs.values() if "graph" in e), None)
+if ent is not None:
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(20):
+        ent["graph"].replay()
+    e.record()
+    torch.cuda.synchronize()
+    print("graph replay alone ms", s.elapsed_time(e) / 20)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        x = pipe._stage_h2d(audio.astype(np.float32))
+    torch.cuda.synchronize()
+    print("pinned stage + H2D ms", (time.perf_counter() - t0) / 20 * 1e3)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        y = ent["out"].cpu().numpy()
+    print("D2H + numpy ms", (time.perf_counter() - t0) / 20 * 1e3)
