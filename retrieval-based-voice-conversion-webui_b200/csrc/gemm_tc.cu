@@ -13,7 +13,7 @@
 
 namespace rvcb {
 
-template <int BN, int BK>
+template <int BN, int BK, bool RS = false>
 struct Cfg {
     static constexpr int A_STAGE = BM * BK * 2;
     static constexpr int B_STAGE_RAW = BN * BK * 2;
@@ -22,29 +22,35 @@ struct Cfg {
     static constexpr int CW = BN >= 32 ? 32 : 16;                 // epilogue chunk width (columns)
     static constexpr int EPI_STRIDE = CW + 4;                     // floats per staged row (16B aligned, conflict-free)
     static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;
-    static constexpr int PIPE_BUDGET = 226 * 1024 - EPI_BYTES - 2048;
+    // RS ("residual staged"): the fp32 residual tile of res1 is TMA-prefetched into 128B-swizzled shared memory while the
+    // tile's MMAs run, so the epilogue of large residual launches issues no global loads (panels of 32 columns x 128 rows)
+    static constexpr int RES_BYTES = RS ? BM * BN * 4 : 0;
+    static constexpr int PIPE_BUDGET = 226 * 1024 - EPI_BYTES - 2048 - RES_BYTES;
     static constexpr int STAGES = (PIPE_BUDGET / STAGE) > 8 ? 8 : (PIPE_BUDGET / STAGE);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int SMEM = STAGES * STAGE + RES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
     static constexpr uint32_t TX_BYTES = A_STAGE + B_STAGE_RAW;
 };
 
-template <int BN, int BK>
+template <int BN, int BK, bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ KParams p) {
-    using C = Cfg<BN, BK>;
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ KParams p) {
+    using C = Cfg<BN, BK, RS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::STAGES * C::A_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint8_t* smem_r = smem + C::STAGES * C::STAGE;                  // residual tile (RS only), 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + C::RES_BYTES);
     uint64_t* full_bar = bars;                      // [STAGES]
     uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
     uint64_t* tfull_bar = bars + 2 * C::STAGES;     // [2]
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-    float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 256);
+    uint64_t* r_full = bars + 2 * C::STAGES + 4;      // [1] residual tile landed
+    uint64_t* r_empty = bars + 2 * C::STAGES + 5;     // [1] residual tile consumed by all epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 6);
+    float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + C::RES_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -59,6 +65,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], (BN / C::CW == 1) ? kEpiWarps / 2 : kEpiWarps);
+        }
+        if (RS) {
+            prefetch_tmap(&tmap_r);
+            mbar_init(r_full, 1);
+            mbar_init(r_empty, kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -76,15 +87,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ======================= TMA producer (warp-uniform loop; one elected lane issues) =======================
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t res_it = 0;                            // RS: tiles whose residual has been requested
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int z = tile / tiles_per_z;
             const int rem = tile - z * tiles_per_z;
             const int mt = rem / p.num_n_tiles;
             const int nt = rem - mt * p.num_n_tiles;
             int kb = 0;
+            // RS: the single residual buffer frees up when the epilogue of the previous tile is done, i.e. some way into this
+            // tile's MMAs: poll for it between operand loads so the operand pipeline never stalls behind it
+            bool res_issued = !RS;
+            auto issue_res = [&]() {
+                if (elect_one()) {
+                    mbar_expect_tx(r_full, (uint32_t)C::RES_BYTES);
+#pragma unroll
+                    for (int pn = 0; pn < BN / 32; ++pn)
+                        tma_load_2d(smem_r + pn * (BM * 128), &tmap_r, r_full, nt * BN + pn * 32, mt * BM);
+                }
+                __syncwarp();
+                res_issued = true;
+            };
             for (int s = 0; s < p.nseg; ++s) {
                 const SegPacked sg = p.seg[s];
                 for (int kc = 0; kc < sg.nk; ++kc, ++kb) {
+                    if (RS && !res_issued && mbar_test(r_empty, (res_it & 1) ^ 1)) issue_res();
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], C::TX_BYTES);
@@ -102,6 +128,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+            }
+            if (RS) {
+                if (!res_issued) {
+                    mbar_wait(r_empty, (res_it & 1) ^ 1);
+                    issue_res();
+                }
+                ++res_it;
             }
         }
     } else if (warp == 1) {
@@ -169,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int m_warp0 = mt * BM + quarter * 32;                // first row of this warp's 32-row slab
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (RS) mbar_wait(r_full, (uint32_t)iter & 1);             // this tile's residual is in shared memory
             const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
             const float* biasz = p.bias ? p.bias + z * p.bias_z : nullptr;
             const float bias_row = (p.bias && p.bias_per_row && (m_warp0 + lane) < p.M) ? p.bias[m_warp0 + lane] : 0.f;
@@ -223,8 +257,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float4 t[NIT];
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) t[it] = *reinterpret_cast<const float4*>(stg + (rsub + RPI * it) * ST + 4 * c4);
-                // residual 1 (before the activation), coalesced
-                if (p.res1) {
+                // residual 1 (before the activation): from the TMA-staged tile (RS), else coalesced from global memory
+                if (RS) {
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int row = quarter * 32 + rsub + RPI * it;               // tile row; panel = chunk c (CW == 32)
+                        const float4 q = *reinterpret_cast<const float4*>(smem_r + c * (BM * 128) + row * 128 + ((c4 ^ (row & 7)) << 4));
+                        t[it].x += q.x; t[it].y += q.y; t[it].z += q.z; t[it].w += q.w;
+                    }
+                } else if (p.res1) {
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) {
                         const int m = m_warp0 + rsub + RPI * it;
@@ -353,7 +394,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                mbar_arrive(&tempty_bar[acc]);
+                if (RS) mbar_arrive(r_empty);              // all of this warp's reads of the residual tile are done
+            }
         }
     }
 
@@ -441,13 +485,14 @@ static std::pair<cudaEvent_t, cudaEvent_t> prof_get() {
     return {a, b};
 }
 
-template <int BN, int BK>
-static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& p, cudaStream_t stream) {
-    using C = Cfg<BN, BK>;
+template <int BN, int BK, bool RS = false>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const KParams& p, cudaStream_t stream) {
+    using C = Cfg<BN, BK, RS>;
+    static_assert(C::STAGES >= 3, "operand ring too shallow");
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         int dev = 0;
         CUDA_CHECK(cudaGetDevice(&dev));
         CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -455,7 +500,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const KParams& 
     }
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (g_prof_on) gemm_prof_record_begin(stream);
-    launch_pdl(gemm_tc_kernel<BN, BK>, grid, kThreads, C::SMEM, stream, ta, tb, p);
+    launch_pdl(gemm_tc_kernel<BN, BK, RS>, grid, kThreads, C::SMEM, stream, ta, tb, tr, p);
     KERNEL_CHECK();
     if (g_prof_on) gemm_prof_record_end(stream, {p.M, p.N, p.total_kb, BK, BN, p.batch, p.nseg, p.num_tiles});
     count_launch();
@@ -539,9 +584,25 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
         encode_map(&tb, g.B, 2, dims, str, box, BK);
     }
 
+    // large launches with an fp32 residual can prefetch the residual tile by TMA (see Cfg::RES_BYTES).  Measured (profiles/README.md,
+    // r1v): neutral on the k = 11 stage-1 convolutions, slower on stage 0 (the 64 KB tile costs two operand-ring stages), so
+    // it is opt-in (RVCB_RS=1) and exercised by tests/test_gemm_gpu.py only.
+    static const bool rs_on = [] { const char* e = getenv("RVCB_RS"); return e && e[0] == '1'; }();
+    const bool rs = rs_on && g.res1 && !g.gate && !g.up2_C && g.batch == 1 && BK == 64 && (BN == 128 || BN == 64) && (g.N % BN) == 0 &&
+                    g.M >= 8192 && (g.ldres1 % 4) == 0 && al(g.res1, 16);
+    CUtensorMap tr = ta;
+    if (rs) {
+        cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+        cuuint64_t str[1] = {(cuuint64_t)g.ldres1 * 4};
+        cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+        encode_map_ex(&tr, g.res1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (BN == 128) { launch<128, 64, true>(ta, tb, tr, p, stream); return; }
+        launch<64, 64, true>(ta, tb, tr, p, stream);
+        return;
+    }
 #define RVCB_LAUNCH(bn, bk)                          \
     if (BN == bn && BK == bk) {                      \
-        launch<bn, bk>(ta, tb, p, stream);           \
+        launch<bn, bk>(ta, tb, tr, p, stream);       \
         return;                                      \
     }
     RVCB_LAUNCH(16, 64) RVCB_LAUNCH(32, 64) RVCB_LAUNCH(64, 64) RVCB_LAUNCH(128, 64)

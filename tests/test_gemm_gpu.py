@@ -342,3 +342,42 @@ def test_weight_stationary_tma_epilogue_variants(epi, cin, k, dil, T, bk):
     assert (t16[:, cout:] == 7.0).all(), "columns past N of the fp16 hand-off buffer must not be touched"
     if epi == 0:
         assert (t32 == 7.0).all()
+
+
+@pytest.mark.parametrize("cin,cout,k,dil,T", [(128, 128, 11, 3, 50001), (256, 256, 3, 1, 19176), (64, 192, 5, 1, 9000)])
+def test_streaming_kernel_with_tma_staged_residual(cin, cout, k, dil, T):
+    """Large launches with an fp32 residual on the streaming kernel, with and without the opt-in TMA prefetch of the residual
+    tile into swizzled shared memory (gemm_tc.cu, RS variant; the env var is read once per process, so this test runs its RS
+    half in a child process): same contract, checked against the SIMT restatement and torch; ragged M tail, 1 / 2 / 3 N-tiles,
+    with and without the second residual."""
+    import os, subprocess, sys
+    if os.environ.get("RVCB_RS") != "1":
+        env = dict(os.environ, RVCB_RS="1")
+        node = f"{__file__}::test_streaming_kernel_with_tma_staged_residual[{cin}-{cout}-{k}-{dil}-{T}]"
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", node], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _setup()
+    from gemm_cases import run_gemm, pack_conv1d
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(77)
+    x = torch.randn(T, cin, device=dev, generator=g).half()
+    w = (torch.randn(cout, cin, k, device=dev, generator=g) / math.sqrt(cin * k)).half()
+    bias = torch.randn(cout, device=dev, generator=g)
+    res = torch.randn(T, cout, device=dev, generator=g)
+    acc = torch.randn(T, cout, device=dev, generator=g)
+    pad = (k - 1) * dil // 2
+    conv = F.conv1d(x.float().t()[None], w.float(), bias, dilation=dil, padding=pad)[0].t()
+    B = pack_conv1d(w, 64).contiguous()
+    segs = [(j * dil - pad, 0, 0, cin // 64) for j in range(k)]
+    for with_res2 in (False, True):
+        ref = conv + res + (acc if with_res2 else 0)
+
+        def run(impl):
+            o32 = torch.zeros(T, cout, device=dev)
+            o16 = torch.zeros(T, cout, device=dev, dtype=torch.half)
+            run_gemm(impl, x, B, T, cout, segs, bias=bias, res1=res, res2=acc if with_res2 else None, act2="lrelu", act2_p=0.1,
+                     out32=o32, ld32=cout, out16=o16, ld16=cout)
+            return o32, o16
+        (t32, t16), (s32, _) = _both(run)
+        _cmp("rs32", t32, ref); _cmp("rs-vs-simt", t32, s32, 1e-4)
+        _cmp("rs16", t16, F.leaky_relu(ref, 0.1), 4e-3)
