@@ -25,10 +25,12 @@ struct Cfg {
     // RS ("residual staged"): the fp32 residual tile of res1 is TMA-prefetched into 128B-swizzled shared memory while the
     // tile's MMAs run, so the epilogue of large residual launches issues no global loads (panels of 32 columns x 128 rows)
     static constexpr int RES_BYTES = RS ? BM * BN * 4 : 0;
-    static constexpr int PIPE_BUDGET = 226 * 1024 - EPI_BYTES - 2048 - RES_BYTES;
-    static constexpr int STAGES = (PIPE_BUDGET / STAGE) > 8 ? 8 : (PIPE_BUDGET / STAGE);
+    static constexpr int PIPE_BUDGET = 226 * 1024 - EPI_BYTES - 2048 - 256 - RES_BYTES;
+    // ring depth: what fits, up to 24 slots -- narrow tiles (BK = 16 / 32: 5-10 KB per slot) need many slots in flight to cover
+    // the ~1 us L2->SMEM latency (8 slots of 5 KB bounded the C = 16 RMVPE layers at 18 B/clk per SM)
+    static constexpr int STAGES = (PIPE_BUDGET / STAGE) > 24 ? 24 : (PIPE_BUDGET / STAGE);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM = STAGES * STAGE + RES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+    static constexpr int SMEM = STAGES * STAGE + RES_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + EPI_BYTES;
     static constexpr uint32_t TX_BYTES = A_STAGE + B_STAGE_RAW;
 };
 
@@ -50,7 +52,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* r_full = bars + 2 * C::STAGES + 4;      // [1] residual tile landed
     uint64_t* r_empty = bars + 2 * C::STAGES + 5;     // [1] residual tile consumed by all epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 6);
-    float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + C::RES_BYTES + 256);
+    float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + C::RES_BYTES + 512);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -518,6 +520,7 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     RVCB_CHECK(g.block_k == 64 || g.block_k == 32 || g.block_k == 16, "gemm: block_k must be 16/32/64");
     RVCB_CHECK(g.out32 || g.out16, "gemm: no output");
     if (gemm_ws_try(g, stream)) return;          // long stride-1 convolutions: weight-stationary halo kernel
+    if (gemm_sk_try(g, stream)) return;          // small-M, long-K launches: cluster split-K
     const int BK = g.block_k;
     int BN = pick_bn(g.N);
     if (BK == 32 && BN > 64) BN = 64;

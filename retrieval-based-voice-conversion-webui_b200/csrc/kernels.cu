@@ -178,77 +178,8 @@ __global__ void softmax_kernel(const float* __restrict__ S, long lds, int T, __h
     }
 }
 
-// Rows of up to 1024 scores: one WARP per row, the row lives in registers (32 values per lane), reductions are shuffles only --
-// no shared memory, no block barrier (the block-per-row kernel above spends its time in 5 __syncthreads per 800-element row).
-__global__ void __launch_bounds__(256) softmax_warp_kernel(const float* __restrict__ S, long lds, int T, long n_rows, __half* __restrict__ P,
-                                                           long ldp, const float* __restrict__ qrel, long ldq, int win,
-                                                           __half* __restrict__ prel) {
-    pdl_trigger();
-    const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= n_rows) return;
-    const int lane = threadIdx.x & 31;
-    const int i = (int)(r % T);
-    const float* sr = S + r * lds;
-    float v[32];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const int j = q * 32 + lane;
-        float x = -INFINITY;
-        if (j < T) {
-            x = sr[j];
-            if (qrel) {
-                const int d = j - i;
-                if (d >= -win && d <= win) x += qrel[r * ldq + d + win];
-            }
-        }
-        v[q] = x;
-        mx = fmaxf(mx, x);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const float e = (q * 32 + lane < T) ? expf(v[q] - mx) : 0.f;
-        v[q] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    __half* pr = P + r * ldp;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-        const int j = q * 32 + lane;
-        if (j < ldp) pr[j] = __float2half_rn(v[q] * inv);      // columns T..ldp-1 are written as zeros (v == 0 there)
-    }
-    if (prel) {
-        // band of +-win around the diagonal, gathered from the lanes that hold those columns
-#pragma unroll
-        for (int half_ = 0; half_ < 2; ++half_) {
-            const int qq = lane + 32 * half_;                   // output slot 0..63
-            const int j = i + qq - win;
-            float pv = 0.f;
-            // every lane must take part in the shuffles: loop over the (at most 3) register rows the band can touch
-            const int jc = min(max(j, 0), T - 1);
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const float got = __shfl_sync(0xffffffffu, v[q], jc & 31);
-                if ((jc >> 5) == q) pv = got;
-            }
-            prel[r * 64 + qq] = __float2half_rn((qq <= 2 * win && j >= 0 && j < T) ? pv * inv : 0.f);
-        }
-    }
-}
-
 void softmax_rows(const float* S, long lds, int H, int T, __half* P, long ldp, const float* qrel, long ldq, int win, __half* prel,
                   cudaStream_t s) {
-    if (T <= 1024 && ldp <= 1024) {
-        const long rows = (long)H * T;
-        softmax_warp_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, s>>>(S, lds, T, rows, P, ldp, qrel, ldq, win, prel);
-        KERNEL_CHECK();
-        count_launch();
-        return;
-    }
     RVCB_CHECK((size_t)T * 4 <= 48 * 1024, "softmax: row too long");
     softmax_kernel<<<H * T, 256, T * sizeof(float), s>>>(S, lds, T, P, ldp, qrel, ldq, win, prel);
     KERNEL_CHECK();

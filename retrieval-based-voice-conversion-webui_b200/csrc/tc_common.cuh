@@ -251,5 +251,7 @@ void gemm_prof_record_end(cudaStream_t stream, const ProfInfo& info);
 
 // weight-stationary halo convolution kernel (gemm_ws.cu); returns false if the launch does not qualify
 bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream);
+// cluster split-K for small-M, long-K launches (gemm_sk.cu); returns false when the launch does not qualify
+bool gemm_sk_try(const GemmArgs& g, cudaStream_t stream);
 
 }  // namespace rvcb
