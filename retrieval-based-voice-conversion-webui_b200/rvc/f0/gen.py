@@ -1,6 +1,7 @@
 """Drop-in for ``rvc.f0.Generator`` (rvc/f0/gen.py:44-141) for the hot path's f0 method: "rmvpe".
-The RMVPE network, mel front end and salience decode run in sm_100a kernels (librvcb200); the O(T)
-resize / gap-fill / mel-quantise post-processing stays on the host like the reference (f0post.py).
+The RMVPE network, mel front end and salience decode run in sm_100a kernels (librvcb200).  ``calculate_device`` keeps the O(T)
+resize / gap-fill / mel-quantise post-processing on the device too (rvcb_f0_post, bit-equal to the host form); ``calculate``
+returns host arrays like the reference and runs that post-processing on the host (f0post.py; needed for manual f0 curves).
 The CPU third-party estimators (pm, dio, harvest, crepe, fcpe) are out of scope."""
 from __future__ import annotations
 

@@ -132,3 +132,21 @@ def test_host_filtfilt_is_scipy_bit_for_bit():
         assert np.array_equal(signal.filtfilt(bh, ah, x64), engine.host_filtfilt(bh, ah, zi, x64)), n
     with pytest.raises(RuntimeError, match="padlen"):
         engine.host_filtfilt(bh, ah, zi, np.zeros(18))
+
+
+def test_highpass_sections_reproduce_the_direct_form_filter():
+    """The device filter's second-order sections (engine.highpass_sos_from_ba) realise the same transfer function as the
+    reference's (bh, ah): denominator reconstructs to 1e-11, and scipy's own sosfiltfilt over them agrees with
+    filtfilt(bh, ah) to 1e-7 on broadband and sub-corner signals."""
+    from scipy import signal
+    from rvc_b200 import engine
+    bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)
+    sos, zi = engine.highpass_sos_from_ba(bh, ah)
+    assert sos.shape == (3, 6) and zi.shape == (3, 2) and np.all(sos[:, 3] == 1.0)
+    a_rec = np.polymul(np.polymul(sos[0, 3:], sos[1, 3:]), sos[2, 3:5])
+    assert np.abs(a_rec - ah).max() < 1e-11
+    rng = np.random.default_rng(2)
+    t = np.arange(48000) / 16000
+    for x in (rng.standard_normal(48000) * 0.3 + 0.05, 0.5 * np.sin(2 * np.pi * 110 * t) + 0.3 * np.sin(2 * np.pi * 30 * t) + 0.1):
+        y = signal.sosfiltfilt(sos, x, padtype="odd", padlen=18)
+        assert np.abs(y - signal.filtfilt(bh, ah, x)).max() < 1e-7
