@@ -76,19 +76,25 @@ class RVC:
             key = (int(wav_dev.shape[0]), int(block_frame_16k), int(skip_head), int(return_length), f0method, float(protect),
                    float(self.f0_up_key), float(self.formant_shift), float(self.index_rate), id(getattr(self, "index", None)))
         ent = self._graphs.get(key) if key is not None else None
-        if ent is None:
-            if key is not None:
+        if ent is not None and "graph" not in ent and not ent.get("failed"):
+            try:
+                ent["x"] = torch.empty_like(wav_dev)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["out"] = self._infer_body(ent["x"], block_frame_16k, skip_head, return_length, f0method, protect)
+                ent["graph"] = g
+                ent["refs"] = (self.net_g, self.hubert, getattr(self, "index", None))     # device pointers are baked into the graph
+            except Exception:                           # capture is an optimisation only: stay eager for this key
+                ent.clear()
+                ent["failed"] = True
+                torch.cuda.synchronize()
+        if ent is None or "graph" not in ent:
+            if key is not None and ent is None:
                 if len(self._graphs) >= 4:
                     self._graphs.pop(next(iter(self._graphs)))
                 self._graphs[key] = {}
             return self._infer_body(wav_dev, block_frame_16k, skip_head, return_length, f0method, protect)
-        if "graph" not in ent:
-            ent["x"] = torch.empty_like(wav_dev)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ent["out"] = self._infer_body(ent["x"], block_frame_16k, skip_head, return_length, f0method, protect)
-            ent["graph"] = g
         ent["x"].copy_(wav_dev, non_blocking=True)
         ent["graph"].replay()
         return ent["out"].clone()

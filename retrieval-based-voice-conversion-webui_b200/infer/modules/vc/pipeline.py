@@ -205,7 +205,7 @@ class Pipeline(object):
         """One-chunk utterance with NO host round trip between the input copy and the result copy: high-pass filtfilt
         (pipeline.py:221), reflect padding (:241), RMVPE, f0 post-processing (rvc/f0/gen.py:10-41), HuBERT + retrieval on a
         side stream, synthesizer, RMS mix + scaling (:349-360) and the int16 cast (modules.py:181) all run on the device.
-        The second time the same (length, settings) comes in, the ~490 launches are captured into a CUDA graph and replayed
+        The second time the same (length, settings) comes in, the ~510 launches are captured into a CUDA graph and replayed
         from then on (RVCB_GRAPHS=0 turns that off).  Returns a device tensor (float32 in the int16 range, or int16)."""
         t0 = time()
         host_ok = getattr(net_g, "accepts_host_scalars", False)
@@ -217,20 +217,30 @@ class Pipeline(object):
             key = (int(audio.shape[0]), id(model), id(net_g), int(sid), float(f0_up_key), id(index), float(index_rate), int(if_f0),
                    int(tgt_sr), float(rms_mix_rate), str(version), float(protect), bool(as_int16))
         ent = self._graphs.get(key) if key is not None else None
-        if key is None or ent is None:
-            if key is not None:
-                if len(self._graphs) >= 4:
-                    self._graphs.pop(next(iter(self._graphs)))
-                self._graphs[key] = {}
-            out = self._dev_body(x, *args)
-        else:
-            if "graph" not in ent:                      # second sighting: capture (arenas and kernels are warm from the first run)
+        if ent is not None and "graph" not in ent and not ent.get("failed"):
+            # second sighting: capture (arenas and kernels are warm from the first run)
+            try:
                 ent["x"] = torch.empty_like(x)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     ent["out"] = self._dev_body(ent["x"], *args)
                 ent["graph"] = g
+            except Exception:                           # capture is an optimisation only: keep launching eagerly for this key
+                logger.warning("CUDA graph capture failed, staying eager:\n%s", traceback.format_exc())
+                ent.clear()
+                ent["failed"] = True
+                torch.cuda.synchronize()
+        if key is None or ent is None or "graph" not in ent:
+            if key is not None and ent is None:
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = {}
+            out = self._dev_body(x, *args)
+        else:
+            if "refs" not in ent:
+                ent["refs"] = (model, net_g, index, big_npy)     # the graph bakes their device pointers in: keep them alive (and
+                                                                 # their id()s, which are part of the key, unrecyclable)
             ent["x"].copy_(x, non_blocking=True)
             ent["graph"].replay()
             out = ent["out"]
