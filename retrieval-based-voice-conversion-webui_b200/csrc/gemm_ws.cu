@@ -724,12 +724,13 @@ static size_t ws_smem_bytes(int BN, int BK, int nseg, int nkc, int HRp) {
 
 // v2 dispatch: the three vocoder epilogue patterns with TMA-legal operands.  Returns false to fall through to v1.
 static bool ws2_try(const GemmArgs& g, cudaStream_t stream, int BK, int nkc, int rmin, int HRp, int m_tiles, int sms, int bo_mode) {
-    static int mode = -1, n32 = 0;
+    static int mode = -1, n32 = 0, n32_off = 0;
     if (mode < 0) {
         const char* e = getenv("RVCB_WS2");
         mode = (e && e[0] == '0') ? 0 : 1;
-        const char* f = getenv("RVCB_WS2_N32");
+        const char* f = getenv("RVCB_WS2_N32");      // 1: narrow slices wherever they fit; 0: never; unset: residual launches only
         n32 = (f && f[0] == '1') ? 1 : 0;
+        n32_off = (f && f[0] == '0') ? 1 : 0;
     }
     if (!mode) return false;
     auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
@@ -751,7 +752,13 @@ static bool ws2_try(const GemmArgs& g, cudaStream_t stream, int BK, int nkc, int
         if (ws2_smem_bytes(cand, BK, g.nseg, nkc, HRp, epi, has_r2, do16) <= 226 * 1024) { BN = cand; break; }
     }
     if (BN == 0) return false;
-    if (BN < 64 && BN < g.N && nkc > 1 && !n32) return false;      // same measured rule as v1 (override: RVCB_WS2_N32=1)
+    // Slices narrower than 64 columns over a multi-chunk C_in re-read the halo tile once per slice and run N = 32 MMAs: measured
+    // slower than the alternatives (k = 7, C = 128: 84 vs 53 us) EXCEPT for residual launches that fit no 64-column variant and
+    // would fall to the streaming kernel, whose epilogue is the bottleneck there (k = 11, C = 128, c2: 119 vs 178 us).
+    if (BN < 64 && BN < g.N && nkc > 1 && !n32) {
+        const bool v1_fits = ws_smem_bytes(64, BK, g.nseg, nkc, HRp) <= 226 * 1024;
+        if (epi == 0 || v1_fits || n32_off) return false;
+    }
     const int n_slices = g.N / BN;
     if (n_slices > sms) return false;
     const int grid = (sms / n_slices) * n_slices;

@@ -298,7 +298,8 @@ def test_conv1d_weight_stationary_halo_kernel(cin, cout, k, dil, T, bk):
 
 
 @pytest.mark.parametrize("epi", [0, 1, 2])
-@pytest.mark.parametrize("cin,k,dil,T,bk", [(64, 11, 5, 80001, 64), (64, 3, 1, 76800, 64), (32, 7, 3, 150017, 32), (128, 3, 1, 90000, 64)])
+@pytest.mark.parametrize("cin,k,dil,T,bk", [(64, 11, 5, 80001, 64), (64, 3, 1, 76800, 64), (32, 7, 3, 150017, 32), (128, 3, 1, 90000, 64),
+                                            (128, 11, 1, 80001, 64)])
 def test_weight_stationary_tma_epilogue_variants(epi, cin, k, dil, T, bk):
     """The three vocoder epilogue patterns of the weight-stationary kernel's TMA-staged epilogue (gemm_ws.cu, v2):
     0: out16 = lrelu(conv + b);  1: y = conv + b + res -> out32, out16 = lrelu(y);  2: y = (conv + b + res)/3 -> out32 only
