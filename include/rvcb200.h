@@ -129,7 +129,7 @@ void rvcb_rmvpe_destroy(rvcb_rmvpe* h);
 typedef struct rvcb_synth_config {
     int inter_channels, hidden_channels, filter_channels, n_heads, n_layers, kernel_size;
     int n_resblock_kernels;  int resblock_kernel_sizes[4];  int resblock_dilations[4][3];
-    int n_upsamples;         int upsample_rates[4];         int upsample_kernel_sizes[4];
+    int n_upsamples;         int upsample_rates[8];         int upsample_kernel_sizes[8];      /* 4 (v2, v1/40k) or 5 (v1/32k, v1/48k) stages */
     int upsample_initial_channel, spk_embed_dim, gin_channels, sr, encoder_dim;
 } rvcb_synth_config;
 int rvcb_synth_create(const rvcb_synth_config* cfg, const rvcb_weights* w, rvcb_synth** out);

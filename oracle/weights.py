@@ -8,4 +8,4 @@ if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
 from rvc_b200.synthetic import *  # noqa: F401,F403,E402
-from rvc_b200.synthetic import HUBERT_CONV, V1_40K_CONFIG, V2_48K_CONFIG, _r16  # noqa: F401,E402
+from rvc_b200.synthetic import HUBERT_CONV, V1_32K_CONFIG, V1_40K_CONFIG, V1_48K_CONFIG, V2_32K_CONFIG, V2_48K_CONFIG, _r16  # noqa: F401,E402

@@ -34,6 +34,7 @@ struct Stage {
     PackedB up; float* up_b; int s, k, cin, cout;
     int noise_k, noise_stride, noise_pad;   // noise conv (nsf.py:176-183), folded into the ups GEMM as extra K columns
     int Mp;                                 // padded count of harmonic-source columns appended to the ups GEMM's A rows (0: no-f0)
+    int dm, bk;                             // polyphase reach (taps -dm..dm) and K block of the upsampling GEMM
     ResBlock rb[4];
 };
 
@@ -77,7 +78,7 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
         DevOwner& own = h->own;
         const int H = c.hidden_channels, F = c.filter_channels, I = c.inter_channels, heads = c.n_heads;
         RVCB_CHECK(H % heads == 0 && H % 8 == 0 && I % 2 == 0, "synth: bad channel config");
-        RVCB_CHECK(c.n_upsamples >= 1 && c.n_upsamples <= 4 && c.n_resblock_kernels >= 1 && c.n_resblock_kernels <= 4, "synth: bad decoder config");
+        RVCB_CHECK(c.n_upsamples >= 1 && c.n_upsamples <= 8 && c.n_resblock_kernels >= 1 && c.n_resblock_kernels <= 4, "synth: bad decoder config");
         const int kc = H / heads, HP = pad_to(kc, 64);
         h->kc = kc; h->HP = HP;
         h->upp = 1;
@@ -201,12 +202,14 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
         for (int i = 0; i < c.n_upsamples; ++i) {
             Stage S{};
             S.s = c.upsample_rates[i]; S.k = c.upsample_kernel_sizes[i]; S.cin = ch; S.cout = ch / 2;
-            RVCB_CHECK(S.k <= 2 * S.s + (S.k - S.s) % 2 && S.k >= S.s, "synth: upsample kernel must satisfy s <= k <= 2s");
+            RVCB_CHECK(S.k >= S.s && (S.k - S.s) % 2 == 0, "synth: upsample kernel must satisfy k >= s with k - s even");
+            S.dm = convT1d_reach(S.k, S.s, (S.k - S.s) / 2);       // input-frame reach of the polyphase form: taps d = -dm..dm
+            S.bk = S.cin >= 64 ? 64 : 32;                           // K block of the upsampling GEMM (5-stage decoders end at C_in = 32)
             const std::string us = "dec.ups." + std::to_string(i);
             const std::vector<float> uw = effective_weight(w, us);
             std::vector<float> ub((size_t)S.s * S.cout);
             const WT& ubias = w.get(us + ".bias");
-            RVCB_CHECK(S.cin % 64 == 0, "synth: upsample input channels must be multiples of 64");
+            RVCB_CHECK(S.cin % S.bk == 0, "synth: upsample input channels must be multiples of 32");
             if (h->use_f0) {
                 const WT& nw = w.get("dec.noise_convs." + std::to_string(i) + ".weight");
                 const WT& nb = w.get("dec.noise_convs." + std::to_string(i) + ".bias");
@@ -219,21 +222,21 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
                 } else {
                     S.noise_stride = 1; S.noise_pad = 0;
                 }
-                S.Mp = round_up((S.s - 1) * S.noise_stride + S.noise_k, 64);
-                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, 64, nw.data.data(), S.noise_k,
+                S.Mp = round_up((S.s - 1) * S.noise_stride + S.noise_k, S.bk);
+                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, S.bk, nw.data.data(), S.noise_k,
                                     S.noise_stride, S.Mp);
                 for (int r = 0; r < S.s; ++r)
                     for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co] + nb.data[co];
             } else {
                 S.Mp = 0;
-                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, 64);
+                S.up = pack_convT1d(own, uw.data(), S.cin, S.cout, S.k, S.s, (S.k - S.s) / 2, S.bk);
                 for (int r = 0; r < S.s; ++r)
                     for (int co = 0; co < S.cout; ++co) ub[(size_t)r * S.cout + co] = ubias.data[co];
             }
             S.up_b = own.upload(ub);
             ch = S.cout;
-            const int bk = ch >= 64 ? 64 : 32;
-            RVCB_CHECK(ch % 32 == 0, "synth: decoder channels must be multiples of 32");
+            const int bk = ch >= 64 ? 64 : (ch >= 32 ? 32 : 16);
+            RVCB_CHECK(ch % 16 == 0, "synth: decoder channels must be multiples of 16");
             for (int j = 0; j < c.n_resblock_kernels; ++j) {
                 ResBlock& R = S.rb[j];
                 R.k = c.resblock_kernel_sizes[j];
@@ -507,7 +510,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     for (int i = 0; i < c.n_upsamples; ++i) {
         const Stage& S = h->stages[i];
         const int Tin = Tt, Tout = Tt * S.s, C = S.cout;
-        const int bk = C >= 64 ? 64 : 32;
+        const int bk = C >= 64 ? 64 : (C >= 32 ? 32 : 16);
         const size_t e = (size_t)Tout * C;
         ar.off = stage_mark;                           // stage scratch is recycled
         __half* prev16 = (i == 0) ? xin16 : carry[(i - 1) & 1];
@@ -526,10 +529,10 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
                         S.noise_pad, st);
         {   // ConvTranspose1d as a polyphase GEMM: [Tin, s*C] == [Tout, C]; + the noise conv as one more K segment.
             // Epilogue emits x (fp32 residual stream) and lrelu(x) (fp16 operand of the first resblock convs).
-            GemmArgs g = mk(prev16, ld_in, Tin, (int)ld_in, S.up, Tin, S.s * C);
-            g.nseg = 3;
-            for (int d = 0; d < 3; ++d) g.seg[d] = {d - 1, 0, 0, S.cin / 64};
-            if (S.Mp) g.seg[g.nseg++] = {0, S.cin, 0, S.Mp / 64};
+            GemmArgs g = mk(prev16, ld_in, Tin, (int)ld_in, S.up, Tin, S.s * C, S.bk);
+            g.nseg = 2 * S.dm + 1;
+            for (int d = 0; d < g.nseg; ++d) g.seg[d] = {d - S.dm, 0, 0, S.cin / S.bk};
+            if (S.Mp) g.seg[g.nseg++] = {0, S.cin, 0, S.Mp / S.bk};
             g.bias = S.up_b; g.out32 = xs32; g.ld32 = (long)S.s * C;
             g.out16 = xs16; g.ld16 = (long)S.s * C; g.act2 = ACT_LRELU; g.act2_p = 0.1f;
             gemm(g, st);

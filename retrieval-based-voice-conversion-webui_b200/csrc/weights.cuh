@@ -95,14 +95,21 @@ inline PackedB pack_conv1d(DevOwner& own, const float* W, int Cout, int Cin, int
 // Optional extra K columns (Mp of them) fold the NSF noise convolution (Conv1d(1, Cout, kn, stride_n) over the harmonic
 // source, nsf.py:176-183) into the same GEMM: the A operand carries har[tin*s*stride_n + m - pad] in column m, and the
 // weight of output phase r at column m is Wn[co, m - r*stride_n].
+// Number of input-frame shifts d = -dm..dm a ConvTranspose1d(k, stride s, padding p) needs: output phase r of frame q reads
+// frame q + d with kernel tap j = r + p - d*s, so dm = max(floor((s - 1 + p) / s), floor((k - 1 - p) / s))  (1 when k < 3s + 2).
+inline int convT1d_reach(int k, int s, int p) {
+    const int hi = (s - 1 + p) / s, lo = (k - 1 - p) / s;
+    return hi > lo ? (hi > 1 ? hi : 1) : (lo > 1 ? lo : 1);
+}
 inline PackedB pack_convT1d(DevOwner& own, const float* W, int Cin, int Cout, int k, int s, int p, int bk = 64,
                             const float* Wn = nullptr, int kn = 0, int stride_n = 0, int Mp = 0) {
+    const int dm = convT1d_reach(k, s, p), ntap = 2 * dm + 1;
     const int Cp = pad_to(Cin, bk), Np = pad_to(s * Cout, 16);
-    const int Kt = 3 * Cp + Mp;
+    const int Kt = ntap * Cp + Mp;
     std::vector<float> h((size_t)Np * Kt, 0.f);
     for (int r = 0; r < s; ++r) {
-        for (int di = 0; di < 3; ++di) {
-            const int j = r + p - (di - 1) * s;
+        for (int di = 0; di < ntap; ++di) {
+            const int j = r + p - (di - dm) * s;
             if (j < 0 || j >= k) continue;
             for (int co = 0; co < Cout; ++co)
                 for (int ci = 0; ci < Cin; ++ci)
@@ -111,7 +118,7 @@ inline PackedB pack_convT1d(DevOwner& own, const float* W, int Cin, int Cout, in
         for (int m = 0; m < Mp && Wn; ++m) {
             const int j = m - r * stride_n;
             if (j < 0 || j >= kn) continue;
-            for (int co = 0; co < Cout; ++co) h[(size_t)(r * Cout + co) * Kt + 3 * Cp + m] = Wn[(size_t)co * kn + j];
+            for (int co = 0; co < Cout; ++co) h[(size_t)(r * Cout + co) * Kt + ntap * Cp + m] = Wn[(size_t)co * kn + j];
         }
     }
     return upload_half(own, h, Np, Kt);

@@ -40,7 +40,7 @@ class SynthConfig(C.Structure):
         ("n_heads", C.c_int), ("n_layers", C.c_int), ("kernel_size", C.c_int),
         ("n_resblock_kernels", C.c_int), ("resblock_kernel_sizes", C.c_int * 4),
         ("resblock_dilations", (C.c_int * 3) * 4),
-        ("n_upsamples", C.c_int), ("upsample_rates", C.c_int * 4), ("upsample_kernel_sizes", C.c_int * 4),
+        ("n_upsamples", C.c_int), ("upsample_rates", C.c_int * 8), ("upsample_kernel_sizes", C.c_int * 8),
         ("upsample_initial_channel", C.c_int), ("spk_embed_dim", C.c_int), ("gin_channels", C.c_int),
         ("sr", C.c_int), ("encoder_dim", C.c_int),
     ]

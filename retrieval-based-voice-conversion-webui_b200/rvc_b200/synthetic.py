@@ -31,6 +31,18 @@ V1_40K_CONFIG = [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11],
                  [16, 16, 4, 4], 109, 256, 40000]
 
 
+# the other decoder schedules of configs/{v1,v2}/*.json: 5-stage decoders (last stage 16 channels), kernel 16 at stride 4 / 6
+V1_48K_CONFIG = [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11],
+                 [[1, 3, 5], [1, 3, 5], [1, 3, 5]], [10, 6, 2, 2, 2], 512,
+                 [16, 16, 4, 4, 4], 109, 256, 48000]
+V1_32K_CONFIG = [513, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11],
+                 [[1, 3, 5], [1, 3, 5], [1, 3, 5]], [10, 4, 2, 2, 2], 512,
+                 [16, 16, 4, 4, 4], 109, 256, 32000]
+V2_32K_CONFIG = [513, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11],
+                 [[1, 3, 5], [1, 3, 5], [1, 3, 5]], [10, 8, 2, 2], 512,
+                 [20, 16, 4, 4], 109, 256, 32000]
+
+
 def _r16(t: torch.Tensor) -> torch.Tensor:
     return t.half().float()
 

@@ -47,6 +47,18 @@ torch.manual_seed(3); ref = net0.infer(phone, torch.tensor([T]), torch.tensor([1
 torch.manual_seed(3); n1 = torch.randn(1, 192, T)
 out = OS.synth_infer(w0, cpt0["config"], phone, torch.tensor([T]), torch.tensor([1]), None, None, n1, None)
 assert out.shape == ref.shape and (out - ref).abs().max().item() < 5e-6
+# the other decoder schedules of configs/{v1,v2}/*.json (5-stage decoders, kernel 16 at stride 4 / 6)
+for cfgx, ver in ((OW.V1_48K_CONFIG, "v1"), (OW.V1_32K_CONFIG, "v1"), (OW.V2_32K_CONFIG, "v2")):
+    cptx = OW.synth_cpt(5, ver, config=cfgx)
+    netx, _ = get_synthesizer({**cptx, "weight": dict(cptx["weight"]), "config": list(cptx["config"])}, "cpu")
+    encx = 256 if ver == "v1" else 768
+    wx = OW.synth_weights(5, cfgx, encx)
+    assert set(netx.state_dict()) == set(wx)
+    Tx = 24; phx = torch.randn(1, Tx, encx, generator=g) * 0.5
+    torch.manual_seed(3); ref = netx.infer(phx, torch.tensor([Tx]), torch.tensor([1]), pitch[:, :Tx], pitchf[:, :Tx])
+    torch.manual_seed(3); n1 = torch.randn(1, 192, Tx); torch.rand(1, 1, 1); n2 = torch.randn(1, Tx * (cfgx[-1] // 100), 1)
+    out = OS.synth_infer(wx, cptx["config"], phx, torch.tensor([Tx]), torch.tensor([1]), pitch[:, :Tx], pitchf[:, :Tx], n1, n2)
+    assert out.shape == ref.shape and (out - ref).abs().max().item() < 5e-6, (cfgx[-1], (out - ref).abs().max().item())
 m = E2E(4, 1, (2, 2)).eval(); rw = OW.rmvpe_weights(9)
 assert set(m.state_dict()) == set(rw)
 m.load_state_dict(rw)

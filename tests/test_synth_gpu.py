@@ -109,3 +109,26 @@ def test_synth_no_f0_model_matches_oracle(rt):
     out = m.infer(phone[0].cuda(), 2, None, None, n1[0].cuda(), None, skip_head, rl, rl).cpu()
     assert out.shape == ref.shape
     assert (out - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("name", ["V1_48K_CONFIG", "V1_32K_CONFIG", "V2_32K_CONFIG"])
+def test_synth_other_decoder_schedules(name):
+    """The remaining configs/{v1,v2}/*.json decoders: 5 upsampling stages ending at 16 channels (v1/32k, v1/48k) and
+    ConvTranspose kernels of 16 at stride 4 / 6 (polyphase reach of 2 / 1 frames), v2/32k's [10, 8, 2, 2] schedule.
+    The oracle is pinned against the reference's SynthesizerTrnMs{256,768}NSFsid on the same configs (<= 5e-7)."""
+    from oracle import synth as OS, weights as OW
+    from rvc_b200.engine import Synth
+    cfg = getattr(OW, name)
+    enc = 256 if name.startswith("V1") else 768
+    w = OW.synth_weights(21, cfg, enc)
+    T = 41
+    phone, pitch, pitchf, g = _inputs(T, seed=13, enc=enc)
+    upp = cfg[-1] // 100
+    n1 = torch.randn(1, 192, T, generator=g)
+    n2 = torch.randn(1, T * upp, 1, generator=g)
+    with torch.no_grad():
+        ref = OS.synth_infer(w, cfg, phone, torch.tensor([T]), torch.tensor([5]), pitch, pitchf, n1, n2)[0, 0]
+    m = Synth(w, cfg, enc)
+    out = m.infer(phone[0].cuda(), 5, pitch[0].cuda(), pitchf[0].cuda(), n1[0].cuda(), n2.reshape(-1).cuda()).cpu()
+    assert out.shape == ref.shape == (T * upp,)
+    assert (out - ref).abs().max().item() <= 1e-3, (out - ref).abs().max().item()
