@@ -59,3 +59,37 @@ def test_hubert_oracle_matches_transformers_golden():
     with torch.no_grad():
         assert np.abs(OH.extract_features(w, wav, 9)[0].numpy() - z["layer9"]).max() < 5e-5
         assert np.abs(OH.extract_features(w, wav, 12)[0].numpy() - z["layer12"]).max() < 5e-5
+
+
+def test_ivf_oracle_against_an_independent_knn():
+    """faiss is absent (un-vendored, un-pinned), so the IVF-Flat oracle *defines* the expected arithmetic; its SEMANTICS
+    (squared-L2 nearest centroid, exact top-8 inside that list, ascending order, ids) are cross-checked here against an
+    independent implementation: scikit-learn's brute-force neighbours in float64 restricted to the probed list.  Index sets
+    must agree wherever the 8th/9th distance gap exceeds float32 resolution; distances to 1e-5 relative."""
+    from sklearn.neighbors import NearestNeighbors
+    from oracle import ivf as OI, weights as OW
+    vec = OW.index_vectors(4000, 768, 3).numpy()
+    idx = OI.build_ivf(vec, None, seed=1, exact_assign=True)
+    rng = np.random.default_rng(0)
+    q = (vec[rng.integers(0, 4000, 60)] + 0.05 * rng.standard_normal((60, 768))).astype(np.float32)
+    D, I = idx.search(q, 8)
+    cen = NearestNeighbors(n_neighbors=1, algorithm="brute", metric="sqeuclidean").fit(idx.centroids.astype(np.float64))
+    lists = cen.kneighbors(q.astype(np.float64), return_distance=False)[:, 0]
+    checked = 0
+    for qi in range(q.shape[0]):
+        a, b = idx.list_off[lists[qi]], idx.list_off[lists[qi] + 1]
+        ids = idx.list_ids[a:b]
+        if len(ids) == 0:
+            assert (I[qi] == -1).all()
+            continue
+        k = min(8, len(ids))
+        nn = NearestNeighbors(n_neighbors=min(k + 1, len(ids)), algorithm="brute", metric="sqeuclidean").fit(vec[ids].astype(np.float64))
+        d64, j = nn.kneighbors(q[qi:qi + 1].astype(np.float64))
+        d64, j = d64[0], ids[j[0]]
+        assert np.all(np.diff(D[qi, :k]) >= 0) and (I[qi, k:] == -1).all()
+        assert np.allclose(D[qi, :k], d64[:k], rtol=1e-5, atol=1e-5)
+        if len(d64) > k and (d64[k] - d64[k - 1]) < 1e-4 * d64[k - 1]:
+            continue                                   # near-tie at the cut: set membership is arithmetic-dependent
+        assert set(I[qi, :k].tolist()) == set(j[:k].tolist()), qi
+        checked += 1
+    assert checked >= 50
