@@ -101,7 +101,7 @@ int rvcb_host_filtfilt(const double* b, const double* a, const double* zi, int n
  * bit: the direct 5th-order form cannot be block-propagated in float64.  d_scratch: >= n + 2*edge + 4120 doubles. */
 int rvcb_sosfiltfilt(const double* sos, const double* zi, int n_sections, int edge, const float* d_x, int64_t n, float* d_y,
                      double* d_scratch, void* stream);
-/* np.pad(x, (pad, pad), mode="reflect") on the device (pipeline.py:241): d_out f32[n + 2*pad], pad < n */
+/* np.pad(x, (pad, pad), mode="reflect") on the device (pipeline.py:241): d_out f32[n + 2*pad]; any pad width (periodic reflection) */
 int rvcb_reflect_pad(const float* d_x, int64_t n, int64_t pad, float* d_out, void* stream);
 /* (int16) x with C truncation, the .astype(np.int16) of modules.py:181: d_out i16[n] */
 int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream);

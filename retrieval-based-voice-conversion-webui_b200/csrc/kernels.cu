@@ -787,13 +787,21 @@ void sosfiltfilt(const SosCoef& c, const float* x, long n, int edge, float* y, d
 __global__ void reflect_pad_1d_kernel(const float* __restrict__ x, long n, long pad, float* __restrict__ out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + 2 * pad) return;
+    // np.pad(mode="reflect") for ANY pad width (a 2 s utterance is shorter than the 3 s pad of the default config): the signal
+    // extended with period 2(n-1), edge samples not repeated
     long j = i - pad;
-    if (j < 0) j = -j;
-    else if (j >= n) j = 2 * (n - 1) - j;
+    const long period = 2 * (n - 1);
+    if (period == 0) {
+        j = 0;
+    } else {
+        j %= period;
+        if (j < 0) j += period;
+        if (j >= n) j = period - j;
+    }
     out[i] = x[j];
 }
 void reflect_pad(const float* x, long n, long pad, float* out, cudaStream_t s) {
-    RVCB_CHECK(pad >= 0 && pad < n, "reflect_pad: pad must be smaller than the signal");
+    RVCB_CHECK(pad >= 0 && n >= 1, "reflect_pad: bad shape");
     reflect_pad_1d_kernel<<<(unsigned)ceil_div_l(n + 2 * pad, 256), 256, 0, s>>>(x, n, pad, out);
     KERNEL_CHECK();
     count_launch();

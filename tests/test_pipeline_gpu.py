@@ -214,7 +214,8 @@ def test_device_front_end_kernels_match_host_dsp():
         got = engine.sosfiltfilt(sos, zi, 18, torch.from_numpy(x).cuda()).cpu().numpy()
         assert np.abs(got - ref).max() <= 2e-7, (n, np.abs(got - ref).max())     # float32 output: half an ulp at |y| ~ 1 is 6e-8
     x = torch.from_numpy(rng.standard_normal(5000).astype(np.float32))
-    assert np.array_equal(engine.reflect_pad(x.cuda(), 48).cpu().numpy(), np.pad(x.numpy(), (48, 48), mode="reflect"))
+    for pad in (0, 48, 4999, 5000, 12345):        # pad >= n: a 2 s utterance under the default 3 s pad (periodic reflection)
+        assert np.array_equal(engine.reflect_pad(x.cuda(), pad).cpu().numpy(), np.pad(x.numpy(), (pad, pad), mode="reflect")), pad
     w = (rng.standard_normal(100000) * 20000).astype(np.float32)
     assert np.array_equal(engine.f32_to_i16(torch.from_numpy(w).cuda()).cpu().numpy(), w.astype(np.int16))
     # f0 contours with leading / interior / trailing unvoiced runs, isolated frames, all-unvoiced, resize up and down
