@@ -1,8 +1,8 @@
 // tcgen05 + TMA implicit-GEMM kernel for sm_100a (see gemm.cuh for the contract).
 //
-// Persistent, warp-specialised CTA of 192 threads, one CTA per SM:
+// Persistent, warp-specialised CTA of 320 threads, one CTA per SM:
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B/64B/32B-swizzled smem ring, mbarrier tx)
-//   warp 1      MMA issuer     (one lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
+//   warp 1      MMA issuer     (warp-uniform loop, one elected lane issues tcgen05.mma kind::f16, fp32 accumulators in TMEM,
 //                               tcgen05.commit releases smem slots / publishes the accumulator)
 //   warps 2..9  epilogue       (tcgen05.ld TMEM -> registers -> warp-private smem transpose -> fused
 //                               bias/act/residual with COALESCED residual loads and output stores)

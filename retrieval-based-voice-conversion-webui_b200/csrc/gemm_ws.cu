@@ -12,6 +12,9 @@
 //   * the epilogue warps prefetch the residual operands of their tile BEFORE waiting for the accumulator, so the
 //     HBM latency of the fp32 residual stream hides under the MMAs.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 epilogue (two groups).
+// Two kernels share that main loop: gemm_ws_kernel (v1: register prefetch of the residual, generic epilogue; used where the
+// TMA staging of v2 does not fit, e.g. C = 128 with k = 7) and gemm_ws2_kernel (v2, further down: every byte of epilogue
+// traffic moves by TMA; the vocoder's three epilogue patterns).
 #include "tc_common.cuh"
 
 namespace rvcb {
