@@ -106,8 +106,23 @@ extern "C" int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const floa
     RVCB_API_END
 }
 
-// scipy.signal.lfilter's float64 loop (direct form II transposed), one pass; z is the state, updated in place
+// scipy.signal.lfilter's float64 loop (direct form II transposed), one pass; z is the state, updated in place.
+// NC known at compile time keeps the state in registers (the recurrence is one add -> mul -> sub dependency chain per sample).
+template <int NC>
+static void lfilter_df2t_fixed(const double* b, const double* a, const double* x, int64_t n, int64_t stride, double* y, double* zio) {
+    double z[NC - 1];
+    for (int k = 0; k < NC - 1; ++k) z[k] = zio[k];
+    for (int64_t i = 0; i < n; ++i) {
+        const double xi = x[i * stride];
+        const double yi = z[0] + b[0] * xi;
+#pragma unroll
+        z[NC - 2] = xi * b[NC - 1] - yi * a[NC - 1];
+        y[i * stride] = yi;
+    }
+    for (int k = 0; k < NC - 1; ++k) zio[k] = z[k];
+}
 static void lfilter_df2t(const double* b, const double* a, int nc, const double* x, int64_t n, int64_t stride, double* y, double* z) {
+    if (nc == 6) return lfilter_df2t_fixed<6>(b, a, x, n, stride, y, z);
     for (int64_t i = 0; i < n; ++i) {
         const double xi = x[i * stride];
         const double yi = z[0] + b[0] * xi;
