@@ -115,7 +115,7 @@ static void lfilter_df2t_fixed(const double* b, const double* a, const double* x
     for (int64_t i = 0; i < n; ++i) {
         const double xi = x[i * stride];
         const double yi = z[0] + b[0] * xi;
-#pragma unroll
+        for (int k = 1; k < NC - 1; ++k) z[k - 1] = z[k] + xi * b[k] - yi * a[k];      // NC is a constant: fully unrolled
         z[NC - 2] = xi * b[NC - 1] - yi * a[NC - 1];
         y[i * stride] = yi;
     }
