@@ -150,3 +150,82 @@ def test_highpass_sections_reproduce_the_direct_form_filter():
     for x in (rng.standard_normal(48000) * 0.3 + 0.05, 0.5 * np.sin(2 * np.pi * 110 * t) + 0.3 * np.sin(2 * np.pi * 30 * t) + 0.1):
         y = signal.sosfiltfilt(sos, x, padtype="odd", padlen=18)
         assert np.abs(y - signal.filtfilt(bh, ah, x)).max() < 1e-7
+
+
+def test_vc_facade_host_logic_with_stub_models(monkeypatch, tmp_path):
+    """The VC facade (infer/modules/vc/modules.py:18-266) without a GPU: Gradio-shaped returns of get_vc, index-path
+    resolution, peak normalisation, the info strings and the exception -> info-string convention of vc_single, and the
+    folder loop of vc_multi (rank striding, per-file log).  Models and pipeline are stubs; nothing here computes audio."""
+    import types
+    from infer.modules.vc import modules as M
+
+    seen = {}
+
+    class FakeNet:
+        def half(self): return self
+        def float(self): return self
+
+    class FakePipeline:
+        def __init__(self, tgt_sr, config):
+            self.tgt_sr = tgt_sr
+
+        def pipeline(self, model, net_g, sid, audio, times, f0_up_key, f0_method, file_index, index_rate, if_f0, *rest):
+            seen.update(audio_peak=float(np.abs(audio).max()), file_index=file_index, want_i16=getattr(self, "_want_int16", None),
+                        f0_up_key=f0_up_key, if_f0=if_f0)
+            if f0_method == "harvest":
+                raise ValueError("f0 method harvest has not yet been supported")
+            times[1] += 0.25
+            return np.linspace(-2000.7, 2000.7, 480).astype(np.float32)
+
+    def fake_get(cpt, device):
+        return FakeNet(), {**cpt, "config": list(cpt["config"])}
+
+    monkeypatch.setattr(M, "Pipeline", FakePipeline)
+    monkeypatch.setattr(M, "get_synthesizer", fake_get)
+    monkeypatch.setattr(M, "load_hubert", lambda device, is_half: "hubert")
+    monkeypatch.setattr(M, "get_index_path_from_model", lambda name: f"logs/{name}/added.index")
+    monkeypatch.setattr(M.torch.cuda, "empty_cache", lambda: None)
+    cfg = types.SimpleNamespace(device="cuda:0", is_half=True)
+    cpt = {"config": [1025, 32, 192, 192, 768, 2, 6, 3, 0, "1", [3, 7, 11], [[1, 3, 5]] * 3, [12, 10, 2, 2], 512, [24, 20, 4, 4], 109, 256, 48000],
+           "weight": {"emb_g.weight": torch.zeros(7, 256)}, "f0": 1, "version": "v2", "info": "200 epochs", "name": "alice.pth"}
+    vc = M.VC(cfg)
+    # no model selected yet: both return shapes of get_vc("")
+    assert vc.get_vc("") == {"visible": True, "maximum": 0, "__type__": "update"}
+    out = vc.get_vc("", 0.4, 0.2, "a.index", "b.index")
+    assert out[0] == {"visible": False, "__type__": "update"} and out[1]["value"] == 0.4 and out[2]["value"] == 0.2
+    assert out[3]["value"] == "a.index" and out[4]["value"] == "b.index" and out[5]["value"] == ""
+    # select a model: speaker count comes from the embedding table, index path from the model name
+    assert vc.get_vc(cpt) == {"visible": True, "maximum": 7, "__type__": "update"}
+    assert (vc.tgt_sr, vc.if_f0, vc.version, vc.n_spk) == (48000, 1, "v2", 7)
+    full = vc.get_vc(cpt, 0.4, 0.2)
+    assert full[0]["maximum"] == 7 and full[1] == {"visible": True, "value": 0.4, "__type__": "update"}
+    assert full[3] == full[4] == {"value": "logs/alice.pth/added.index", "__type__": "update"} and full[5]["value"] == "200 epochs"
+    # one utterance: loud input is scaled to a 0.95 peak, the text-box index wins over the dropdown and is cleaned up
+    audio = np.full(32000, 3.0, dtype=np.float32)
+    info, (sr, wav) = vc.vc_single(0, audio, "2", None, "rmvpe", ' "logs/x/trained_IVF1_Flat.index"\n', "logs/y/added.index", 0.75, 3, 0, 0.25, 0.33)
+    assert info == "Success.\nIndex not used.\nTime: npy: 0.00s, f0: 0.25s, infer: 0.00s." and sr == 48000
+    assert wav.dtype == np.int16 and wav[0] == -2000 and wav[-1] == 2000          # C truncation, like .astype(np.int16)
+    assert abs(seen["audio_peak"] - 0.95) < 1e-6 and seen["file_index"] == "logs/x/added_IVF1_Flat.index"
+    assert seen["want_i16"] is True and vc.pipeline._want_int16 is False and seen["f0_up_key"] == 2 and vc.hubert_model == "hubert"
+    ipath = tmp_path / "added.index"
+    ipath.write_bytes(b"x")
+    info, _ = vc.vc_single(0, audio.copy(), 0, None, "rmvpe", "", str(ipath), 0.75, 3, 0, 0.25, 0.33)
+    assert f"Index: {ipath}." in info and seen["file_index"] == str(ipath)
+    info, _ = vc.vc_single(0, audio.copy(), 0, None, "rmvpe", None, "", 0.75, 3, 44100, 0.25, 0.33)
+    assert seen["file_index"] == "" and _[0] == 44100                                # resample_sr >= 16000 and != tgt_sr is reported
+    # errors become the info string; a missing input is its own message
+    assert vc.vc_single(0, audio.copy(), 0, None, "harvest", "", "", 0.75, 3, 0, 0.25, 0.33) == ("f0 method harvest has not yet been supported", None)
+    assert vc.vc_single(0, None, 0, None, "rmvpe", "", "", 0.75, 3, 0, 0.25, 0.33) == ("You need to upload an audio", None)
+    # a folder: every file of this rank, cumulative log, audio written next to it
+    indir, outdir = tmp_path / "in", tmp_path / "out"
+    indir.mkdir()
+    for n in ("a.wav", "b.wav", "c.wav"):
+        (indir / n).write_bytes(b"")
+    saved = []
+    monkeypatch.setattr(M, "load_audio", lambda path, sr: np.zeros(16000, np.float32) + 0.1)
+    monkeypatch.setattr(M, "save_audio", lambda path, wav, sr, f32=False: saved.append((os.path.basename(path), sr, wav.dtype)))
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    msgs = list(vc.vc_multi(0, f' "{indir}" ', str(outdir), [], 0, "rmvpe", "", "", 0.75, 3, 0, 0.25, 0.33, "flac"))
+    assert outdir.is_dir() and len(saved) == len(os.listdir(indir)[1::2]) and all(s[0].endswith(".flac") and s[1] == 48000 for s in saved)
+    assert msgs[-1].count("->Success.") == len(saved) and msgs[-1] == msgs[-2]
