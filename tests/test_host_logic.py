@@ -229,3 +229,60 @@ def test_vc_facade_host_logic_with_stub_models(monkeypatch, tmp_path):
     msgs = list(vc.vc_multi(0, f' "{indir}" ', str(outdir), [], 0, "rmvpe", "", "", 0.75, 3, 0, 0.25, 0.33, "flac"))
     assert outdir.is_dir() and len(saved) == len(os.listdir(indir)[1::2]) and all(s[0].endswith(".flac") and s[1] == 48000 for s in saved)
     assert msgs[-1].count("->Success.") == len(saved) and msgs[-1] == msgs[-2]
+
+
+def test_training_side_extraction_scripts_host_logic(tmp_path):
+    """Drop-ins for infer/modules/train/extract_{feature,f0}_print.py (SURVEY 8f-4): file discovery, [i::n] striding,
+    skip-if-present, output names / shapes / dtypes and the log lines, with stub models (the arithmetic behind them is the
+    HuBERT / RMVPE path of the inference tests)."""
+    from infer.modules.train import extract_f0_print as XF0, extract_feature_print as XFE
+    exp = tmp_path / "exp"
+    wavs = exp / "1_16k_wavs"
+    wavs.mkdir(parents=True)
+    for n in ("0_0.wav", "0_1.wav", "0_2.wav", "0_3.wav", "notes.txt", "0_4.spec.wav"):
+        (wavs / n).write_bytes(b"")
+
+    class FakeHubert:
+        def __init__(self): self.calls = []
+        def extract_features(self, source, padding_mask, output_layer):
+            assert source.shape[0] == 1 and padding_mask.shape == source.shape and not padding_mask.any()
+            self.calls.append(output_layer)
+            T = source.shape[1] // 320
+            x = torch.full((1, T, 768), float(len(self.calls)))
+            if len(self.calls) == 2:
+                x[0, 0, 0] = float("nan")
+            return x, None
+        def final_proj(self, x): return x[..., :256]
+
+    lines = []
+    load = lambda p: np.zeros(3200, np.float32)
+    m = FakeHubert()
+    n = XFE.run(m, str(exp), "v2", 2, 0, load, lines.append)            # rank 0 of 2: files 0, 2, 4 of the sorted listing
+    mine = sorted(os.listdir(wavs))[0::2]
+    assert m.calls == [12] * sum(f.endswith(".wav") for f in mine)
+    assert lines[0] == "all-feature-%d" % len(mine) and lines[-1] == "all-feature-done" and any("contains nan" in l for l in lines)
+    out = sorted(os.listdir(exp / "3_feature768"))
+    assert n == len(out) and all(f.endswith(".npy") for f in out) and "0_0.npy" in out
+    assert np.load(exp / "3_feature768" / "0_0.npy").shape == (10, 768)
+    lines.clear()
+    assert XFE.run(FakeHubert(), str(exp), "v2", 2, 0, load, lines.append) <= 1     # existing outputs are skipped (only the NaN file is retried)
+    m1 = FakeHubert()
+    XFE.run(m1, str(exp), "v1", 1, 0, load, lines.append)
+    assert m1.calls and set(m1.calls) == {9} and np.load(exp / "3_feature256" / "0_0.npy").shape == (10, 256)
+    assert XFE.run(FakeHubert(), str(exp), "v2", 64, 63, load, lines.append) == 0 and lines[-1] == "no-feature-todo"
+
+    class FakeF0:
+        def calculate(self, x, p_len, key, method, radius, manual=None):
+            assert (p_len, key, method) == (x.shape[0] // 160, 0, "rmvpe")
+            return np.full(p_len, 42, np.int32), np.full(p_len, 220.0)
+
+    jobs = XF0.list_jobs(str(exp))
+    assert [os.path.basename(j[0]) for j in jobs] == ["0_0.wav", "0_1.wav", "0_2.wav", "0_3.wav", "notes.txt"]     # "spec" files are skipped
+    lines.clear()
+    assert XF0.run(FakeF0(), jobs[:4], "rmvpe", load, lines.append) == 4
+    assert lines[0] == "todo-f0-4" and lines[1].startswith("f0ing,now-0,all-4,-")
+    c, f = np.load(exp / "2a_f0" / "0_1.wav.npy"), np.load(exp / "2b-f0nsf" / "0_1.wav.npy")
+    assert c.dtype == np.int32 and c.shape == f.shape == (20,) and c[0] == 42 and f[0] == 220.0
+    assert XF0.run(FakeF0(), jobs[:4], "rmvpe", load, lines.append) == 0          # both outputs present -> skipped
+    assert XF0.run(FakeF0(), [], "rmvpe", load, lines.append) == 0 and lines[-1] == "no-f0-todo"
+    assert XFE.main(["x"]) == 0                                                    # wrong arity: silently exit 0 like the reference
