@@ -286,3 +286,38 @@ def test_training_side_extraction_scripts_host_logic(tmp_path):
     assert XF0.run(FakeF0(), jobs[:4], "rmvpe", load, lines.append) == 0          # both outputs present -> skipped
     assert XF0.run(FakeF0(), [], "rmvpe", load, lines.append) == 0 and lines[-1] == "no-f0-todo"
     assert XFE.main(["x"]) == 0                                                    # wrong arity: silently exit 0 like the reference
+
+
+def test_faiss_container_reader_variants(tmp_path):
+    """The IwFl reader on the variants faiss itself writes besides our own writer's: sparse list-size table ("sprs", used when
+    most lists are empty), an array direct map, and the refusals (other index types, inner-product metric)."""
+    import struct
+    from rvc_b200 import faiss_io
+    d, nlist = 8, 6
+    rng = np.random.default_rng(0)
+    cent = rng.standard_normal((nlist, d)).astype("<f4")
+    vec = rng.standard_normal((5, d)).astype("<f4")
+    lists = {1: [3, 0], 4: [2, 4, 1]}                                  # list -> ids (4 of 6 lists empty)
+
+    def hdr(dd, nt, metric=1): return struct.pack("<iqqqBi", dd, nt, 1 << 20, 1 << 20, 1, metric)
+
+    def build(fourcc=b"IwFl", metric=1):
+        b = fourcc + hdr(d, 5, metric) + struct.pack("<QQ", nlist, 1)
+        b += b"IxF2" + hdr(d, nlist) + struct.pack("<Q", cent.size) + cent.tobytes()
+        b += struct.pack("<BQ", 1, 5) + np.arange(5, dtype="<i8").tobytes()           # direct map type 1 (array) with 5 entries
+        b += b"ilar" + struct.pack("<QQ", nlist, 4 * d) + b"sprs" + struct.pack("<Q", 2 * len(lists))
+        b += b"".join(struct.pack("<QQ", l, len(ids)) for l, ids in lists.items())
+        for l, ids in lists.items():
+            b += vec[ids].tobytes() + np.asarray(ids, dtype="<i8").tobytes()
+        return b
+    p = tmp_path / "added_IVF6_Flat_nprobe_1_x_v2.index"
+    p.write_bytes(build())
+    lay = faiss_io.read_index(str(p))
+    assert np.array_equal(lay.centroids, cent) and np.array_equal(lay.vectors, vec)
+    assert lay.list_off.tolist() == [0, 0, 2, 2, 2, 5, 5] and lay.list_ids.tolist() == [3, 0, 2, 4, 1]
+    p.write_bytes(build(fourcc=b"IxF2"))
+    with pytest.raises(ValueError, match="unsupported faiss index type"):
+        faiss_io.read_index(str(p))
+    p.write_bytes(build(metric=0))
+    with pytest.raises(ValueError, match="METRIC_L2"):
+        faiss_io.read_index(str(p))
