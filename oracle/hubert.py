@@ -46,7 +46,7 @@ def pos_conv_weight(w: W) -> torch.Tensor:
 
 def conv_feature_extractor(w: W, wav: torch.Tensor) -> torch.Tensor:
     """wav [B, N] -> [B, 512, T_h]"""
-    x = wav.unsqueeze(1)
+    x = wav.unsqueeze(1).to(w["feature_extractor.conv_layers.0.0.weight"].dtype)
     for i, (_c, _k, s) in enumerate(HUBERT_CONV):
         x = F.conv1d(x, w[f"feature_extractor.conv_layers.{i}.0.weight"], None, stride=s)
         if i == 0:
@@ -79,7 +79,7 @@ def extract_features(w: W, source: torch.Tensor, output_layer: int = 12,
     """fairseq HubertModel.extract_features(source, padding_mask=all-False, mask=False,
     output_layer=L)[0]: [B, T_h, 768] (no final_proj; v1 callers apply it,
     pipeline.py:110)."""
-    f = conv_feature_extractor(w, source.float())
+    f = conv_feature_extractor(w, source)
     x = f.transpose(1, 2)
     x = F.layer_norm(x, (512,), w["layer_norm.weight"], w["layer_norm.bias"], 1e-5)
     x = F.linear(x, w["post_extract_proj.weight"], w["post_extract_proj.bias"])

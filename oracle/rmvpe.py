@@ -49,11 +49,11 @@ def mel_filterbank(sr=SR, n_fft=N_FFT, n_mels=N_MELS, fmin=30.0, fmax=8000.0) ->
 
 def log_mel(wav: torch.Tensor) -> torch.Tensor:
     """wav f32 [B, N] -> log-mel [B, 128, N//160 + 1]  (mel.py:51-71, fp32 path)."""
-    win = torch.hann_window(N_FFT)
+    win = torch.hann_window(N_FFT, device=wav.device)
     fft = torch.stft(wav, n_fft=N_FFT, hop_length=HOP, win_length=N_FFT, window=win, center=True,
                      return_complex=True)
     mag = torch.sqrt(fft.real.pow(2) + fft.imag.pow(2))
-    mel = torch.matmul(torch.from_numpy(mel_filterbank()), mag)
+    mel = torch.matmul(torch.from_numpy(mel_filterbank()).to(mag.device), mag)
     return torch.log(torch.clamp(mel, min=1e-5))
 
 
@@ -67,6 +67,20 @@ def _cbr(w: W, p: str, x):
     if p + "shortcut.weight" in w:
         return y + F.conv2d(x, w[p + "shortcut.weight"], w[p + "shortcut.bias"])
     return y + x
+
+
+_GRU_CACHE: dict = {}
+
+
+def _gru_module(w: W) -> torch.nn.GRU:
+    """torch.nn.GRU carrying the fc.0.gru.* weights (deepunet BiGRU, e2e.py:8-67), built once per weight dict."""
+    ref = w["fc.0.gru.weight_ih_l0"]
+    key = (id(w), ref.device, ref.dtype)
+    if key not in _GRU_CACHE:
+        gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True)
+        gru.load_state_dict({k[len("fc.0.gru."):]: v for k, v in w.items() if k.startswith("fc.0.gru.")})
+        _GRU_CACHE[key] = gru.to(device=ref.device, dtype=ref.dtype).eval()
+    return _GRU_CACHE[key]
 
 
 def e2e_forward(w: W, mel: torch.Tensor, n_blocks=4, en_de=5, inter=4, taps: Optional[dict] = None) -> torch.Tensor:
@@ -99,10 +113,7 @@ def e2e_forward(w: W, mel: torch.Tensor, n_blocks=4, en_de=5, inter=4, taps: Opt
     x = x.transpose(1, 2).flatten(-2)                       # [B,T,384]
     if taps is not None:
         taps["gru_in"] = x
-    gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True)
-    sd = {k[len("fc.0.gru."):]: v for k, v in w.items() if k.startswith("fc.0.gru.")}
-    gru.load_state_dict(sd)
-    x = gru(x)[0]
+    x = _gru_module(w)(x)[0]
     if taps is not None:
         taps["gru_out"] = x
     return torch.sigmoid(F.linear(x, w["fc.1.weight"], w["fc.1.bias"]))
@@ -113,7 +124,7 @@ def mel2hidden(w: W, mel: torch.Tensor) -> torch.Tensor:
     n_pad = 32 * ((n_frames - 1) // 32 + 1) - n_frames
     if n_pad > 0:
         mel = F.pad(mel, (0, n_pad), mode="constant")
-    return e2e_forward(w, mel.float())[:, :n_frames]
+    return e2e_forward(w, mel.to(w["cnn.weight"].dtype))[:, :n_frames]
 
 
 def decode(salience: np.ndarray, thred: float = 0.03) -> np.ndarray:

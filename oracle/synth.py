@@ -51,17 +51,17 @@ def rel_attention(w: W, p: str, x: torch.Tensor, mask: torch.Tensor, n_heads: in
     ek = w[p + "emb_rel_k"][0]                             # [2w+1, kc]
     ev = w[p + "emb_rel_v"][0]
     rel = q @ ek.t()                                       # [B,H,T,2w+1]
-    idx = torch.arange(T)
+    idx = torch.arange(T, device=x.device)
     d = idx[None, :] - idx[:, None]                        # j - i
     band = d.abs() <= window
     di = (d + window).clamp(0, 2 * window)
-    scores = scores + torch.where(band, rel.gather(-1, di.expand(B, n_heads, T, T)), torch.zeros(()))
+    scores = scores + torch.where(band, rel.gather(-1, di.expand(B, n_heads, T, T)), torch.zeros((), device=x.device, dtype=rel.dtype))
     am = mask.unsqueeze(2) * mask.unsqueeze(-1)            # [B,1,T,T]
     scores = scores.masked_fill(am == 0, -1e4)
     pr = F.softmax(scores, dim=-1)
     out = pr @ v
-    pband = torch.where(band, pr, torch.zeros(()))         # [B,H,T,T]
-    relw = torch.zeros(B, n_heads, T, 2 * window + 1)
+    pband = torch.where(band, pr, torch.zeros((), device=x.device, dtype=pr.dtype))         # [B,H,T,T]
+    relw = torch.zeros(B, n_heads, T, 2 * window + 1, device=x.device, dtype=pr.dtype)
     relw.scatter_add_(-1, di.expand(B, n_heads, T, T), pband)
     out = out + relw @ ev
     out = out.transpose(2, 3).contiguous().view(B, C, T)
@@ -77,7 +77,7 @@ def text_encoder(w: W, phone, pitch, lengths, n_heads=2, n_layers=6, ksz=3, skip
     x = F.leaky_relu(x, 0.1)
     x = x.transpose(1, -1)
     T = x.shape[2]
-    mask = (torch.arange(T)[None, :] < lengths[:, None]).unsqueeze(1).to(x.dtype)
+    mask = (torch.arange(T, device=x.device)[None, :] < lengths.to(x.device)[:, None]).unsqueeze(1).to(x.dtype)
     x = x * mask
     x = x * mask   # Encoder.forward re-applies (encoders.py:66)
     for i in range(n_layers):
@@ -132,7 +132,7 @@ def sine_source(w: W, f0: torch.Tensor, upp: int, sr: int, noise: torch.Tensor):
     """generators.py:148-194 + nsf.py:57-61.  f0 [B,T]; noise [B,T*upp,1] ~ N(0,1).
     Returns har_source [B,1,T*upp]."""
     f0 = f0.unsqueeze(-1)
-    a = torch.arange(1, upp + 1, dtype=f0.dtype)
+    a = torch.arange(1, upp + 1, dtype=f0.dtype, device=f0.device)
     rad = f0 / sr * a                                         # [B,T,upp]
     rad2 = torch.fmod(rad[:, :-1, -1:].float() + 0.5, 1.0) - 0.5
     rad_acc = rad2.cumsum(dim=1).fmod(1.0).to(f0)
@@ -143,7 +143,8 @@ def sine_source(w: W, f0: torch.Tensor, upp: int, sr: int, noise: torch.Tensor):
     uv = F.interpolate(uv.transpose(2, 1), scale_factor=float(upp), mode="nearest").transpose(2, 1)
     noise_amp = uv * 0.003 + (1 - uv) * 0.1 / 3
     sw = sines * uv + noise_amp * noise
-    har = torch.tanh(F.linear(sw, w["dec.m_source.l_linear.weight"], w["dec.m_source.l_linear.bias"]))
+    lw = w["dec.m_source.l_linear.weight"]
+    har = torch.tanh(F.linear(sw.to(lw.dtype), lw, w["dec.m_source.l_linear.bias"]))
     return har.transpose(1, 2)
 
 

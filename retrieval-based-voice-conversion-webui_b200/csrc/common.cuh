@@ -70,11 +70,26 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 struct Arena {
     char* base = nullptr;
     size_t cap = 0, off = 0, high = 0;
+    unsigned generation = 0;          // bumped on every growth (diagnostics / tests)
+    char* retired[24] = {};           // outgrown blocks, kept alive until the handle dies
+    int n_retired = 0;
+    // Growth never frees: CUDA graphs captured by the Python front doors (Pipeline / rtrvc.RVC) bake arena addresses
+    // into their kernel nodes, and a graph for an earlier, shorter shape may be replayed after a longer utterance made
+    // the arena grow.  The outgrown block stays allocated (its layout for that shape is still self-consistent: the
+    // arena is reset at the start of every call), growth is geometric (>= 1.5x) so the retired blocks sum to < 2x cap.
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
-        if (base) CUDA_CHECK(cudaFree(base));
-        CUDA_CHECK(cudaMalloc(&base, bytes));
-        cap = bytes;
+        size_t want = bytes;
+        if (cap) want = bytes > cap + cap / 2 ? bytes : cap + cap / 2;
+        char* nb = nullptr;
+        CUDA_CHECK(cudaMalloc(&nb, want));
+        if (base) {
+            if (n_retired < 24) retired[n_retired++] = base;
+            else CUDA_CHECK(cudaFree(base));          // unreachable in practice: 24 geometric growths = 16000x
+        }
+        base = nb;
+        cap = want;
+        ++generation;
     }
     void reset() { off = 0; }
     template <typename T>
@@ -88,6 +103,7 @@ struct Arena {
     }
     ~Arena() {
         if (base) cudaFree(base);
+        for (int i = 0; i < n_retired; ++i) cudaFree(retired[i]);
     }
 };
 

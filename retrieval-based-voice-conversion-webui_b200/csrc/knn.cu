@@ -12,6 +12,7 @@
 #include "api_macros.h"
 #include "common.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace rvcb;
@@ -30,8 +31,10 @@ struct rvcb_index {
     // workspace
     unsigned long long* best = nullptr;
     int best_cap = 0;
+    std::vector<unsigned long long*> retired;     // outgrown workspaces (see ensure_ws)
     ~rvcb_index() {
         cudaFree(centroids); cudaFree(vectors); cudaFree(list_off); cudaFree(list_ids); cudaFree(best);
+        for (auto* p : retired) cudaFree(p);
     }
 };
 
@@ -225,11 +228,16 @@ static void top1(const float* db, long long n, int d, const float* q, int nq, un
     count_launch();
 }
 
+// The coarse-assignment workspace grows geometrically and the outgrown block is kept until the index dies: a CUDA graph
+// captured for a shorter utterance still points at it (see Arena::reserve).
 static void ensure_ws(rvcb_index* ix, int nq) {
     if (nq > ix->best_cap) {
-        cudaFree(ix->best);
-        CUDA_CHECK(cudaMalloc(&ix->best, sizeof(unsigned long long) * nq));
-        ix->best_cap = nq;
+        const int want = std::max(nq, ix->best_cap + ix->best_cap / 2);
+        unsigned long long* nb = nullptr;
+        CUDA_CHECK(cudaMalloc(&nb, sizeof(unsigned long long) * want));
+        if (ix->best) ix->retired.push_back(ix->best);
+        ix->best = nb;
+        ix->best_cap = want;
     }
 }
 
@@ -301,10 +309,10 @@ int rvcb_knn_bruteforce_top1(const float* d_db, int64_t n, int d, const float* d
     cudaStream_t st = (cudaStream_t)stream;
     static unsigned long long* ws = nullptr;
     static int ws_cap = 0;
-    if (nq > ws_cap) {
-        cudaFree(ws);
-        CUDA_CHECK(cudaMalloc(&ws, sizeof(unsigned long long) * nq));
-        ws_cap = nq;
+    if (nq > ws_cap) {      // outgrown blocks are leaked on purpose (a captured graph may still reference them); geometric growth
+        const int want = std::max(nq, ws_cap + ws_cap / 2);
+        CUDA_CHECK(cudaMalloc(&ws, sizeof(unsigned long long) * want));
+        ws_cap = want;
     }
     top1(d_db, n, d, d_q, nq, ws, st);
     unpack_best_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(ws, nq, d_D, (long long*)d_I, nullptr);

@@ -162,13 +162,24 @@ class Pipeline(object):
         return ix, ix.vectors
 
     def _stage_h2d(self, audio: np.ndarray) -> torch.Tensor:
-        """One pinned-memory H2D copy of the utterance (float32), asynchronous on the current stream."""
+        """One pinned-memory H2D copy of the utterance (float32), asynchronous on the current stream.  Two staging buffers
+        alternate, each guarded by the event of the last copy issued from it: back-to-back calls without a host sync never
+        overwrite a buffer whose queued copy has not run yet."""
         n = int(audio.shape[0])
-        if self._pinned is None or self._pinned.numel() < n:
-            self._pinned = torch.empty(max(n, 1 << 18), dtype=torch.float32, pin_memory=True)
-        stage = self._pinned[:n]
+        if self._pinned is None or self._pinned[0][0].numel() < n:
+            cap = max(n, 1 << 18)
+            self._pinned = [[torch.empty(cap, dtype=torch.float32, pin_memory=True), None] for _ in range(2)]
+            self._pin_i = 0
+        self._pin_i ^= 1
+        slot = self._pinned[self._pin_i]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        stage = slot[0][:n]
         stage.numpy()[:] = audio          # casts float64 -> float32 if needed
-        return stage.to(self.device, non_blocking=True)
+        x = stage.to(self.device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream())
+        return x
 
     def _dev_body(self, x, model, net_g, sid, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version,
                   protect, as_int16):

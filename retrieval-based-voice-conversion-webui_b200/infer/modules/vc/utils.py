@@ -20,15 +20,34 @@ class _Permissive:
     def __setstate__(self, s): self.__dict__.update(s if isinstance(s, dict) else {})
 
 
+# Globals a tensor checkpoint legitimately needs.  Everything else pickled inside a fairseq checkpoint (Dictionary, argparse
+# Namespace, omegaconf nodes, ...) is mapped to an inert stub UNCONDITIONALLY: find_class never imports on behalf of the file,
+# so a crafted hubert_base.pt cannot reach os.system / subprocess / builtins.eval (the reference's inference-side load uses
+# torch safe_globals for the same reason, infer/modules/vc/utils.py:24-36).
+_ALLOWED_GLOBALS = {
+    ("collections", "OrderedDict"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._tensor", "_rebuild_from_type_v2"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch.serialization", "_get_layout"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("_codecs", "encode"),
+}
+_ALLOWED_TORCH_NAMES = {n for n in dir(torch) if n.endswith("Storage")} | {
+    "float16", "float32", "float64", "bfloat16", "int8", "int16", "int32", "int64", "uint8", "bool"}
+
+
 def _load_fairseq_state_dict(path: str) -> dict:
+    import importlib
     import pickle
 
     class U(pickle.Unpickler):
         def find_class(self, module, name):
-            try:
-                return super().find_class(module, name)
-            except Exception:
-                return type(name, (_Permissive,), {})
+            if (module, name) in _ALLOWED_GLOBALS or (module == "torch" and name in _ALLOWED_TORCH_NAMES):
+                return getattr(importlib.import_module(module), name)
+            return type(name, (_Permissive,), {})
 
     class PM:
         Unpickler = U

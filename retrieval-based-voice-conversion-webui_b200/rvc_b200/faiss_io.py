@@ -87,16 +87,31 @@ def read_index(path: str) -> IVFLayout:
         sizes[pairs[:, 0].astype(np.int64)] = pairs[:, 1]
     else:
         raise ValueError(f"unsupported list encoding {lt!r}")
+    # structural validation: the device kernels index vectors[id * d] and list_ids[list_off[l]..] unchecked
+    if nl != nlist or qn != nlist or qd != d:
+        raise ValueError(f"inconsistent index file: nlist {nlist} / quantizer {qn}x{qd} / lists {nl} / d {d}")
+    if code_size != 4 * d:
+        raise ValueError(f"code_size {code_size} != 4*d: not a Flat (float32) inverted list")
+    if int(sizes.sum()) != ntotal:
+        raise ValueError(f"list sizes sum to {int(sizes.sum())}, header says ntotal = {ntotal}")
+    if nprobe != 1:
+        raise ValueError(f"index stores nprobe = {nprobe}; the search here is nprobe = 1 (the WebUI writes nprobe 1, web.py:564-571)")
     vectors = np.zeros((ntotal, d), dtype=np.float32)
-    list_ids = np.empty(ntotal, dtype=np.int64)
+    list_ids = np.full(ntotal, -1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    seen = np.zeros(ntotal, dtype=bool)
     for l in range(nl):
         k = int(sizes[l])
         if k == 0: continue
         codes = np.frombuffer(r.take(k * code_size), dtype="<f4").reshape(k, d)
         ids = np.frombuffer(r.take(8 * k), dtype="<i8")
+        if ids.min() < 0 or ids.max() >= ntotal:
+            raise ValueError(f"list {l}: vector id outside [0, {ntotal})")
         list_ids[off[l]:off[l + 1]] = ids
         vectors[ids] = codes
+        seen[ids] = True
+    if not seen.all():
+        raise ValueError("index file does not hold every id in [0, ntotal) exactly once (reconstruct_n would be undefined)")
     return IVFLayout(centroids, vectors, off, list_ids, int(nprobe))
 
 

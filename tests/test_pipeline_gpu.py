@@ -43,15 +43,19 @@ def test_pipeline_matches_oracle_with_shared_pitch_and_noise():
     times = [0, 0, 0]
     out = pipe.pipeline(hub, net_g, 0, audio.copy(), times, 0, (pitch, pitchf.astype(np.float64)), gidx, 0.75, 2, 3, 48000, 0, 0.25, "v2", 0.33)
     assert out.shape == ref.shape
-    # retrieval indices: HuBERT feature error (~1e-2) can flip near-ties; require >= 97 % identical neighbours
+    # retrieval indices: the nearest neighbour (the argmax index) must be the oracle's on every frame; fp16-operand feature
+    # noise (3e-4 mean) may flip a few near-ties among ranks 2..8
     feats = hub.extract_features(source=torch.from_numpy(np.pad(__import__("scipy.signal").signal.filtfilt(
         __import__("infer.modules.vc.pipeline", fromlist=["bh"]).bh, __import__("infer.modules.vc.pipeline", fromlist=["ah"]).ah, audio),
         (16000, 16000), mode="reflect").astype(np.float32))[None].cuda(), output_layer=12)[0][0]
     _, I = gidx.search_device(feats, 8)
-    same = (I.cpu().numpy() == op.taps[0]["ix"]).mean()
-    assert same >= 0.97, same
+    I = I.cpu().numpy()
+    assert np.array_equal(I[:, 0], op.taps[0]["ix"][:, 0])
+    same = (I == op.taps[0]["ix"]).mean()
+    assert same >= 0.98, same
     err = np.abs(out - ref).max() / 32768.0
-    assert err < 2e-2, f"end-to-end max abs err (full scale) {err}"
+    print(f"[parity] 2 s utterance: all-8 neighbours same {same:.4f}, e2e max abs err {err:.3e}")
+    assert err < 2e-3, f"end-to-end max abs err (full scale) {err}"
     # 2) the full path with its own RMVPE f0: coarse pitch agrees on >= 95 % of frames, f0 within 1 % where both voiced
     c2, f2 = pipe.f0_gen.calculate(np.pad(__import__("scipy.signal").signal.filtfilt(
         __import__("infer.modules.vc.pipeline", fromlist=["bh"]).bh, __import__("infer.modules.vc.pipeline", fromlist=["ah"]).ah, audio),
@@ -140,7 +144,9 @@ def test_pipeline_multichunk_long_audio_matches_oracle():
         net_g.set_noise(*tp["noise"])
     out = pipe.pipeline(HubertB200(hw, "cuda:0"), net_g, 0, audio.copy(), [0, 0, 0], 0, (pitch, pitchf), "", 0.0, 2, 3, 48000, 0, 1.0, "v2", 0.5)
     assert out.shape == ref.shape
-    assert np.abs(out - ref).max() / 32768.0 < 2e-2
+    err = np.abs(out - ref).max() / 32768.0
+    print(f"[parity] multi-chunk 7 s utterance: e2e max abs err {err:.3e}")
+    assert err < 2e-3, err
 
 
 def test_vc_single_with_index_file_and_vc_multi(tmp_path):
