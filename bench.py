@@ -260,7 +260,7 @@ def main():
     gms, gn = C.c_double(0), C.c_ulonglong(0)
     _lib.check(_lib.lib().rvcb_prof_end(C.byref(gms), C.byref(gn)))
     gemm_ms_per_step = gms.value / 3
-    cls = [(C.c_double * 2)() for _ in range(4)]
+    cls = [(C.c_double * 3)() for _ in range(4)]
     _lib.check(_lib.lib().rvcb_prof_classes(*cls))
     ws_ms, ws_n, ws_flops, ws_bytes = cls[0][1] / 3, cls[1][1] / 3, cls[2][1] / 3, cls[3][1] / 3
     pk, pk_src = peaks()

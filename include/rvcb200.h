@@ -35,9 +35,10 @@ const char* rvcb_version(void);
 /* per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline); begin resets, end syncs and sums */
 int rvcb_prof_begin(void);
 int rvcb_prof_end(double* gemm_ms, unsigned long long* gemm_launches);
-/* per-kernel-class totals of the last profiled region; each array has 2 entries: [0] streaming gemm_tc_kernel, [1] weight-stationary
- * gemm_ws_kernel (ms, launches, 2*M*N*K flops incl. K padding, algorithmic HBM bytes (WS only)) */
-int rvcb_prof_classes(double* ms2, double* launches2, double* flops2, double* bytes2);
+/* per-kernel-class totals of the last profiled region; each array has 3 entries: [0] streaming gemm_tc_kernel (+ split-K), [1] weight-
+ * stationary gemm_ws*_kernel, [2] fused residual-block kernel (ms, launches, 2*M*N*K flops incl. K padding, algorithmic HBM bytes
+ * (classes 1 and 2)) */
+int rvcb_prof_classes(double* ms3, double* launches3, double* flops3, double* bytes3);
 
 /* ---- weight container (host fp32 tensors keyed by the reference's state_dict names) ------
  * replaces: torch.load + load_state_dict in rvc/synthesizer.py:10-35, rvc/f0/models.py:9-11,
@@ -156,6 +157,14 @@ typedef struct rvcb_gemm_desc {
 } rvcb_gemm_desc;
 /* impl: 0 = tcgen05/TMA kernel (product), 1 = SIMT restatement (validation only) */
 int rvcb_op_gemm(const rvcb_gemm_desc* d, int impl, void* stream);
+
+/* ---- op-level entry for the unit tests: the fused residual block of the vocoder -------------
+ * replaces: ResBlock1.forward (rvc/layers/residuals.py:68-85): for d in dil: x = x + c2(lrelu(c1_d(lrelu(x, 0.1)), 0.1)).
+ * Host weights w1[i], w2[i]: f32 [C, C, k] (weight-norm folded), b1[i], b2[i]: f32 [C]; i = 0..2.  d_x f32 [T, C] (channels last);
+ * d_y f32 [rvcb_op_resblock1_out_rows(...), C] (the kernel stores whole tiles; rows >= T are scratch).  C in {32, 64, 128}. */
+int64_t rvcb_op_resblock1_out_rows(int C, int k, const int* dil, int T);
+int rvcb_op_resblock1(int C, int k, const int* dil, const float* const* w1, const float* const* b1, const float* const* w2,
+                      const float* const* b2, const float* d_x, int T, float* d_y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -200,6 +200,23 @@ extern "C" int rvcb_f0_post(const float* d_f0, int n_frames, int p_len, double k
     RVCB_API_END
 }
 
+#include "resblock_fused.cuh"
+extern "C" int64_t rvcb_op_resblock1_out_rows(int C, int k, const int* dil, int T) {
+    if (!dil || !rvcb::resblock_fused_supported(C, k, dil)) return -1;
+    return rvcb::resblock_fused_out_rows(C, k, dil, T);
+}
+extern "C" int rvcb_op_resblock1(int C, int k, const int* dil, const float* const* w1, const float* const* b1, const float* const* w2,
+                                 const float* const* b2, const float* d_x, int T, float* d_y, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(dil && w1 && b1 && w2 && b2 && d_x && d_y && T > 0, "null argument");
+    RVCB_CHECK(rvcb::resblock_fused_supported(C, k, dil), "resblock1: unsupported (C, k, dilations)");
+    rvcb::DevOwner own;       // test entry: packs on every call
+    const rvcb::RBFusedWeights w = rvcb::pack_resblock_fused(own, C, k, dil, w1, b1, w2, b2);
+    rvcb::resblock_fused(w, d_x, d_y, T, (cudaStream_t)stream);
+    CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    RVCB_API_END
+}
+
 extern "C" int rvcb_prof_classes(double* ms2, double* launches2, double* flops2, double* bytes2) {
     RVCB_API_BEGIN
     RVCB_CHECK(ms2 && launches2 && flops2 && bytes2, "null argument");

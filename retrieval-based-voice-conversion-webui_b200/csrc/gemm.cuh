@@ -75,8 +75,8 @@ void gemm(const GemmArgs& g, cudaStream_t stream);
 
 void gemm_prof_begin();
 void gemm_prof_end(double* ms_total, unsigned long long* launches);
-// per-class totals of the last profiled region: [0] streaming kernel, [1] weight-stationary kernel
-void gemm_prof_classes(double ms[2], double launches[2], double flops[2], double bytes[2]);
+// per-class totals of the last profiled region: [0] streaming kernel, [1] weight-stationary kernel, [2] fused residual block
+void gemm_prof_classes(double ms[3], double launches[3], double flops[3], double bytes[3]);
 
 // helpers to fill segments
 inline void seg_linear(GemmArgs& g, int K) {

@@ -450,13 +450,13 @@ void gemm_prof_end(double* ms_total, unsigned long long* launches) {
     if (ms_total) *ms_total = tot;
     if (launches) *launches = g_prof_events.size();
 }
-void gemm_prof_classes(double ms[2], double launches[2], double flops[2], double bytes[2]) {
-    for (int c = 0; c < 2; ++c) ms[c] = launches[c] = flops[c] = bytes[c] = 0;
+void gemm_prof_classes(double ms[3], double launches[3], double flops[3], double bytes[3]) {
+    for (int c = 0; c < 3; ++c) ms[c] = launches[c] = flops[c] = bytes[c] = 0;
     for (size_t i = 0; i < g_prof_events.size() && i < g_prof_info.size(); ++i) {
         float t = 0;
         cudaEventElapsedTime(&t, g_prof_events[i].first, g_prof_events[i].second);
         const ProfInfo& q = g_prof_info[i];
-        const int c = q.BN < 0 ? 1 : 0;
+        const int c = q.BN <= -1000 ? 2 : (q.BN < 0 ? 1 : 0);
         ms[c] += t;
         launches[c] += 1;
         flops[c] += 2.0 * q.M * q.N * (double)q.kb * q.BK * q.batch;

@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include <algorithm>
 #include "kernels.cuh"
+#include "resblock_fused.cuh"
 #include "weights.cuh"
 
 #include <cmath>
@@ -29,6 +30,7 @@ struct ResBlock {
     PackedB c1[3], c2[3];
     float *b1[3], *b2[3];
     int k, dil[3];
+    RBFusedWeights fused;      // the six convolutions packed for the one-launch kernel (resblock_fused.cu); C == 0: not available
 };
 struct Stage {
     PackedB up; float* up_b; int s, k, cin, cout;
@@ -37,6 +39,18 @@ struct Stage {
     int dm, bk;                             // polyphase reach (taps -dm..dm) and K block of the upsampling GEMM
     ResBlock rb[4];
 };
+
+// RVCB_FUSED: comma-separated channel counts that use the fused residual-block kernel ("0" = none); default below
+bool fused_mask(int C) {
+    static int m32 = -1, m64 = 0, m128 = 0;
+    if (m32 < 0) {
+        const char* e = getenv("RVCB_FUSED");
+        const std::string v = e ? e : "32,64";
+        auto has = [&](const char* t) { return ("," + v + ",").find(std::string(",") + t + ",") != std::string::npos; };
+        m32 = has("32"); m64 = has("64"); m128 = has("128");
+    }
+    return C == 32 ? m32 : (C == 64 ? m64 : (C == 128 ? m128 : 0));
+}
 
 GemmArgs mk(const __half* A, long lda, int a_rows, int a_cols, const PackedB& B, int M, int N, int bk = 64) {
     GemmArgs g;
@@ -241,15 +255,21 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
                 ResBlock& R = S.rb[j];
                 R.k = c.resblock_kernel_sizes[j];
                 const std::string rp = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j) + ".";
+                std::vector<float> ew1[3], ew2[3];
+                const float *pw1[3], *pw2[3], *pb1[3], *pb2[3];
                 for (int q = 0; q < 3; ++q) {
                     R.dil[q] = c.resblock_dilations[j][q];
-                    const std::vector<float> w1 = effective_weight(w, rp + "convs1." + std::to_string(q));
-                    const std::vector<float> w2 = effective_weight(w, rp + "convs2." + std::to_string(q));
-                    R.c1[q] = pack_conv1d(own, w1.data(), ch, ch, R.k, bk);
-                    R.c2[q] = pack_conv1d(own, w2.data(), ch, ch, R.k, bk);
-                    R.b1[q] = own.upload(w.get(rp + "convs1." + std::to_string(q) + ".bias").data);
-                    R.b2[q] = own.upload(w.get(rp + "convs2." + std::to_string(q) + ".bias").data);
+                    ew1[q] = effective_weight(w, rp + "convs1." + std::to_string(q));
+                    ew2[q] = effective_weight(w, rp + "convs2." + std::to_string(q));
+                    R.c1[q] = pack_conv1d(own, ew1[q].data(), ch, ch, R.k, bk);
+                    R.c2[q] = pack_conv1d(own, ew2[q].data(), ch, ch, R.k, bk);
+                    const WT& wb1 = w.get(rp + "convs1." + std::to_string(q) + ".bias");
+                    const WT& wb2 = w.get(rp + "convs2." + std::to_string(q) + ".bias");
+                    R.b1[q] = own.upload(wb1.data);
+                    R.b2[q] = own.upload(wb2.data);
+                    pw1[q] = ew1[q].data(); pw2[q] = ew2[q].data(); pb1[q] = wb1.data.data(); pb2[q] = wb2.data.data();
                 }
+                if (resblock_fused_supported(ch, R.k, R.dil)) R.fused = pack_resblock_fused(own, ch, R.k, R.dil, pw1, pb1, pw2, pb2);
             }
             h->stages.push_back(S);
         }
@@ -304,7 +324,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             mx = std::max(mx, 3 * rnd(e * 4) + 4 * rnd(e * 2));
         }
         carry_e = std::max(carry_e, (size_t)Tt * ch);
-        need += mx + 2 * rnd(carry_e * 2);
+        need += mx + 2 * rnd(carry_e * 2) + (16u << 20);     // + whole-tile slack of the fused residual-block outputs
     }
     h->arena.reserve(need);
     h->arena.reset();
@@ -515,12 +535,24 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
         ar.off = stage_mark;                           // stage scratch is recycled
         __half* prev16 = (i == 0) ? xin16 : carry[(i - 1) & 1];
         __half* next16 = carry[i & 1];
+        const int nk = c.n_resblock_kernels;
+        // One launch per residual block (resblock_fused.cu) where the kernel has a variant and the sequence is long enough to fill
+        // the machine with whole tiles; short sequences (the realtime block) keep the layer-by-layer kernels, whose M tiles are finer.
+        bool fused = fused_mask(C) && (size_t)Tout >= 64u * (size_t)resblock_fused_tile_rows(C);
+        for (int j = 0; j < nk && fused; ++j) fused = S.rb[j].fused.C == C;
         float* xs32 = ar.alloc<float>(e);
-        float* y32 = ar.alloc<float>(e);
-        float* sum32 = ar.alloc<float>(e);
-        __half* xs16 = ar.alloc<__half>(e);
-        __half* y16 = ar.alloc<__half>(e);
-        __half* t16 = ar.alloc<__half>(e);
+        float *y32 = nullptr, *sum32 = nullptr, *yb[4] = {nullptr, nullptr, nullptr, nullptr};
+        __half *xs16 = nullptr, *y16 = nullptr, *t16 = nullptr;
+        if (fused) {
+            for (int j = 0; j < nk; ++j)
+                yb[j] = ar.alloc<float>((size_t)resblock_fused_out_rows(C, S.rb[j].k, S.rb[j].dil, Tout) * C);
+        } else {
+            y32 = ar.alloc<float>(e);
+            sum32 = ar.alloc<float>(e);
+            xs16 = ar.alloc<__half>(e);
+            y16 = ar.alloc<__half>(e);
+            t16 = ar.alloc<__half>(e);
+        }
         const long ld_in = S.cin + S.Mp;
         const bool last_stage = (i + 1 == c.n_upsamples);
         const long ld_next = last_stage ? C : (C + h->stages[i + 1].Mp);
@@ -534,10 +566,16 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             for (int d = 0; d < g.nseg; ++d) g.seg[d] = {d - S.dm, 0, 0, S.cin / S.bk};
             if (S.Mp) g.seg[g.nseg++] = {0, S.cin, 0, S.Mp / S.bk};
             g.bias = S.up_b; g.out32 = xs32; g.ld32 = (long)S.s * C;
-            g.out16 = xs16; g.ld16 = (long)S.s * C; g.act2 = ACT_LRELU; g.act2_p = 0.1f;
+            if (!fused) { g.out16 = xs16; g.ld16 = (long)S.s * C; g.act2 = ACT_LRELU; g.act2_p = 0.1f; }
             gemm(g, st);
         }
-        const int nk = c.n_resblock_kernels;
+        if (fused) {
+            for (int j = 0; j < nk; ++j) resblock_fused(S.rb[j].fused, xs32, yb[j], Tout, st);
+            resblock_mean_lrelu(yb, nk, Tout, C, next16, ld_next, last_stage ? 0.01f : 0.1f, st);
+            carry16 = next16;
+            Tt = Tout;
+            continue;
+        }
         // Branch order: widest kernel first.  The mean over branches is order-independent, and this way the branch whose
         // resident weights are largest needs neither the running-sum tile nor the fp16 hand-off tile in shared memory.
         int order[4] = {0, 1, 2, 3};
