@@ -11,7 +11,12 @@ SynthesizerTrnMs768NSFsid.infer -> RMS mix + int16.
   e2e     VC.vc_single (the reference's public entry) with HOST numpy audio in and host int16 audio out:
           pinned H2D of the utterance, the same body, D2H of the int16 result, all host work inside the timed region
   --impl reference   the reference's CPU path (oracle restatement, pinned against the reference's own modules)
-                     on the box's host cores for the same metric/config.
+                     on the box's host cores for the same metric/config: each step is ONE FULL utterance (all 16 s of model
+                     compute), thread count chosen by a short sweep over {16, 32, 64, 128}.
+  --impl reference_gpu   SURVEY section 8d(ii): the same PyTorch modules EAGER on this GPU (cuDNN / cuBLAS), fp16 and fp32, with the
+                     reference's host round trips preserved (oracle/gpu_ref.py) -- the same-box bar the sm_100a kernels must beat.
+Before timing, the default run checks its own output: the product path with the oracle's pitch track and noise draws against the
+fp32 CPU oracle's waveform of the same utterance (the cpu_baseline leg computes it anyway): "parity_check" in the JSON line.
 Synthetic seeded weights / audio / index (no assets, no network): "data": "synthetic".
 """
 from __future__ import annotations
@@ -77,59 +82,110 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-CPU_SAMPLE_SECONDS = 2.0      # seconds of MODEL compute per CPU sample (the 10 s utterance is 16 s of compute at x_pad=3)
+WORKLOAD = "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)"
+METRIC = "48kHz audio samples/sec (v2/48k infer, RMVPE, IVF index)"
 
 
-def make_cpu_sample(audio, idx):
-    """A bounded sample of the same workload for the CPU arm: a CPU_SAMPLE_SECONDS-long slice of the padded utterance goes
-    through the whole reference path (RMVPE f0 -> HuBERT -> IVF search + blend -> synthesizer); credited output samples =
-    the slice's share of the utterance's 479 040 samples (per-second work is identical, attention is the only
-    super-linear term and favours the short slice)."""
-    from scipy import signal
-    from oracle import pipeline as OP, rmvpe as ORM, weights as OW
-    pipe = OP.OraclePipeline(48000, 3, 10, 60, 65, OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234), OW.V2_48K_CONFIG)
-    a = signal.filtfilt(OP.bh, OP.ah, audio)
-    audio_pad = np.pad(a, (48000, 48000), mode="reflect").astype(np.float32)
-    n = int(CPU_SAMPLE_SECONDS * 16000)
-    chunk = np.ascontiguousarray(audio_pad[96000: 96000 + n])
-    big = idx.reconstruct_n(0, idx.ntotal)
-    credit = OUT_SAMPLES * n / audio_pad.shape[0]
+def make_cpu_pipeline(noise_seed=3):
+    from oracle import pipeline as OP, weights as OW
+    return OP.OraclePipeline(48000, 3, 10, 60, 65, OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234), OW.V2_48K_CONFIG,
+                             noise_seed=noise_seed)
 
-    def step():
-        with torch.no_grad():
-            pitch, pitchf = ORM.calculate(pipe.rw, chunk, n // 160, 0)
-            pt = torch.tensor(pitch).unsqueeze(0).long()
-            pf = torch.tensor(pitchf.astype(np.float32)).unsqueeze(0)
-            return pipe.vc(torch.tensor([0]), chunk, pt, pf, idx, big, 0.75, "v2", 0.33)
-    return step, credit
+
+def cpu_full_step(pipe, audio, idx):
+    """ONE full utterance through the whole reference path on the host (filtfilt, reflect pad, RMVPE f0 + post-processing, HuBERT,
+    IVF search + blend, synthesizer, RMS mix, scaling): pipeline.py:186-366 as restated by the oracle."""
+    pipe.taps.clear()
+    with torch.no_grad():
+        return pipe.pipeline(0, audio.copy(), 0, "rmvpe", idx, 0.75, 1, 48000, 0, 0.25, "v2", 0.33)
+
+
+def pick_cpu_threads(pipe, audio, idx):
+    """Thread sweep on a 1.5 s slice of the utterance (the convolutions are small: more threads is not always faster)."""
+    from oracle import rmvpe as ORM
+    n = os.cpu_count()
+    cands = sorted({c for c in (16, 32, 64, 128) if c <= n} | {min(n, 16)})
+    chunk = np.ascontiguousarray(audio[: 24000])
+    res = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                pitch, pitchf = ORM.calculate(pipe.rw, chunk, 150, 0)
+                pipe.vc(torch.tensor([0]), chunk, torch.tensor(pitch).unsqueeze(0).long(), torch.tensor(pitchf.astype(np.float32)).unsqueeze(0),
+                        None, None, 0.0, "v2", 0.33)
+            best = min(best, time.perf_counter() - t0)
+        res[c] = best
+    pipe.taps.clear()
+    c = min(res, key=res.get)
+    torch.set_num_threads(c)
+    return c, {str(k): round(v, 3) for k, v in res.items()}
 
 
 def reference_arm(args, rank, world):
-    """The reference's own CPU implementation of the path (oracle restatement) on the host cores."""
+    """The reference's own CPU implementation of the path (oracle restatement) on the host cores, one full utterance per step."""
     if rank != 0:
         return
-    from oracle import ivf as OI, pipeline as OP, weights as OW
-    cores = min(os.cpu_count(), 16)        # more threads than this only adds fork/join overhead on these small convolutions
-    torch.set_num_threads(cores)
+    from oracle import gpu_ref as GR, ivf as OI, weights as OW
     audio = OW.synth_voice(UTT_SECONDS, seed=0).numpy()
     vec = OW.index_vectors(100000, 768, 0).numpy()
-    idx = OI.build_ivf(vec, None, seed=0, exact_assign=False)
-    step, credit = make_cpu_sample(audio, idx)
+    # faiss is absent: a BLAS-backed IVF search (what faiss-cpu does for nq >= 20) stands in, not the oracle's serial lane-order scan
+    idx = GR.BlasIVF(OI.build_ivf(vec, None, seed=0, exact_assign=False))
+    idx.ntotal = vec.shape[0]
+    idx.reconstruct_n = lambda i0, n: vec[i0:i0 + n]
+    pipe = make_cpu_pipeline()
+    cores, sweep = pick_cpu_threads(pipe, audio, idx)
     for _ in range(args.warmup):
-        step()
+        cpu_full_step(pipe, audio, idx)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cpu_full_step(pipe, audio, idx)
     dt = time.perf_counter() - t0
-    v = args.steps * credit / dt
-    line = {"impl": "reference", "metric": "48kHz audio samples/sec (v2/48k infer, RMVPE, IVF index)", "value": v, "unit": "samples/s",
+    v = args.steps * OUT_SAMPLES / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "rtf_x": v / 48000.0,
-            "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)"},
+            "rtf_x": v / 48000.0, "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"each step = a {CPU_SAMPLE_SECONDS:g} s slice (of 16 s) of the padded utterance through the whole reference path, credited {credit:.0f} output samples; torch CPU fp32, {cores} threads of {os.cpu_count()} cores"},
+                             "sample": f"each step = ONE FULL utterance (16 s of model compute, {OUT_SAMPLES} output samples) through the whole reference path; "
+                                       f"torch CPU fp32, {cores} threads of {os.cpu_count()} cores (sweep, s per 1.5 s slice: {sweep}); IVF search by BLAS (faiss absent)"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def reference_gpu_arm(args, rank, world):
+    """the oracle's functional PyTorch modules eager on the GPU (cuDNN / cuBLAS), host round trips preserved."""
+    if rank != 0:
+        return
+    from oracle import gpu_ref as GR, ivf as OI, weights as OW
+    torch.set_num_threads(min(os.cpu_count(), 32))
+    audio = OW.synth_voice(UTT_SECONDS, seed=0).numpy()
+    idx = OI.build_ivf(OW.index_vectors(100000, 768, 0).numpy(), None, seed=0, exact_assign=False)
+    res = {}
+    for half in (True, False):
+        g = GR.GpuReference(OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234), OW.V2_48K_CONFIG, idx, "cuda:0", half, 3)
+        for _ in range(max(args.warmup, 2)):
+            g.convert(audio.copy())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g.convert(audio.copy())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        g.convert(audio.copy(), timed=True)
+        res["fp16" if half else "fp32"] = {"ms_per_step": dt * 1e3, "samples_per_s": OUT_SAMPLES / dt, "stages_ms": {k: round(v, 2) for k, v in g.stage_ms.items()}}
+        del g
+        torch.cuda.empty_cache()
+    v = res["fp16"]["samples_per_s"]
+    line = {"impl": "reference_gpu", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["fp16"]["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (the reference's is_half GPU default, configs/config.py:38); fp32 alongside", "data": "synthetic",
+            "config": {"workload": WORKLOAD}, "variants": res,
+            "note": "oracle modules (pinned against the reference's own) eager on the same GPU: cuDNN / cuBLAS kernels, host round trips of "
+                    "pipeline.py:118,135-138,172-174 and rmvpe.py:109 preserved, IVF search on the host by BLAS (faiss absent); wall clock, host in -> host out",
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": int(256000 * 4 * 2 + 799 * 768 * 4), "d2h_bytes_per_step": int(1601 * 360 * 4 + 799 * 768 * 4 + 767040 * 4)}}
     print(json.dumps(line), flush=True)
 
 
@@ -138,7 +194,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -146,6 +202,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.impl == "reference_gpu":
+        reference_gpu_arm(args, rank, world)
         return
     if args.warmup < 3:          # timing hygiene: never fewer than 3 untimed warm-up steps (reported as run)
         args.warmup = 3
@@ -252,6 +311,32 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- BASELINE config #3 (realtime gui.py block: 160 ms at 48 kHz, extra 2.5 s, crossfade 0.05 s): per-block latency of
+    # rtrvc.RVC.infer + the device-side callback tail (envelope mix + SOLA, gui.py:1024-1087) + D2H of the output block ----
+    realtime = None
+    if world == 1:
+        from infer.lib.rtrvc import RVC
+        from infer.modules.gui import RealtimeTail
+        tail = RealtimeTail(48000, 0.16, 0.05, 2.5, str(dev))
+        rt = RVC(0, 0, SY.synth_cpt(1234, "v2"), index, 0.75, device=str(dev), hubert_model=vc.hubert_model, rmvpe_state_dict=cfg.rmvpe_state_dict)
+        nblk, nwarm = 300, 20
+        stream16 = SY.synth_voice(2.72 + 0.16 * (nblk + nwarm) + 0.1, seed=5).to(dev)
+        inp48 = SY.synth_voice(0.25, sr=48000, seed=6).to(dev)
+        lat = []
+        for b in range(nblk + nwarm):
+            win = stream16[b * tail.block_frame_16k: b * tail.block_frame_16k + tail.input_frames_16k]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            y = rt.infer(win, tail.block_frame_16k, tail.skip_head, tail.return_length, "rmvpe")
+            out_blk = tail.process(y, inp48, 0.0)            # gui.py default rms_mix_rate 0 -> envelope mix on
+            out_blk.cpu()                                    # the callback copies the block to the output ring (gui.py:1088-1094)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.array(lat[nwarm:])
+        realtime = {"config": "configs[2]: 160 ms blocks, 43520-sample 16 kHz window, skip_head 250, return_length 21, v2/48k + RMVPE + 100k index",
+                    "blocks": int(nblk), "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()),
+                    "block_period_ms": 160.0, "what": "rtrvc.RVC.infer + RealtimeTail.process (envelope mix + SOLA) + D2H of the 7680-sample block, wall clock"}
+        del rt, tail
+
     # ---- roofline of the dominant kernel family (gemm_tc): live CUDA events around every launch of one step set ----
     import ctypes as C
     _lib.check(_lib.lib().rvcb_prof_begin())
@@ -263,19 +348,21 @@ def main():
     cls = [(C.c_double * 3)() for _ in range(4)]
     _lib.check(_lib.lib().rvcb_prof_classes(*cls))
     ws_ms, ws_n, ws_flops, ws_bytes = cls[0][1] / 3, cls[1][1] / 3, cls[2][1] / 3, cls[3][1] / 3
+    fu_ms, fu_n, fu_flops, fu_bytes = cls[0][2] / 3, cls[1][2] / 3, cls[2][2] / 3, cls[3][2] / 3
     pk, pk_src = peaks()
     achieved = ALGO_FLOPS / (gemm_ms_per_step * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    voc_ms, voc_flops = fu_ms + ws_ms, fu_flops + ws_flops
 
     value = world * args.steps * OUT_SAMPLES / (dev_ms * 1e-3)
     e2e_v = world * args.steps * OUT_SAMPLES / (e2e_ms * 1e-3)
     line = {
-        "metric": "48kHz audio samples/sec (v2/48k infer, RMVPE, IVF index)", "value": value, "unit": "samples/s",
+        "metric": METRIC, "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate+residuals",
         "data": "synthetic", "rtf_x_per_gpu": value / world / 48000.0,
-        "config": {"workload": "configs[1]: v2/48k, RMVPE f0, 100k-vec IVF2564,Flat k=8 rate 0.75, 10s utterance, x_pad=3 (16s compute)",
-                   "l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1,
+        "config": {"workload": WORKLOAD},
+        "timing": {"l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1,
                    "device_step": f"CUDA graph replay of the {int(launches)}-launch step" if use_graph else "eager launches"},
         "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(160000 * 4 + 8),   # the utterance (float32, one pinned copy) + speaker id
                 "d2h_bytes_per_step": int(OUT_SAMPLES * 2),  # mixed + normalised waveform, int16
@@ -284,37 +371,77 @@ def main():
         "gpu_launches": int(launches * args.steps),
         "gpu_launches_per_step": int(launches),
         "clocks": sampler.summary(),
-        # dominant kernel by work: the weight-stationary vocoder convolution (44 % of the utterance's FLOPs); it is HBM-bound
-        # in this unfused layer-by-layer design: algorithmic bytes = activations in + weights + fp32 residual in + outputs
-        "roofline": {"bound": "hbm", "achieved": ws_bytes / (ws_ms * 1e-3) / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
-                     "frac": ws_bytes / (ws_ms * 1e-3) / 1e9 / pk.get("hbm_gbs"),
-                     "traffic": 244.0e6, "traffic_note": "dram read+write of one stage-2 c2 launch (ncu --set full, profiles/prof_r1u_ws2_metrics.txt: 147.4 MB read + 96.6 MB written, 47.2 us) vs 294 MB algorithmic; part of the fp16/fp32 output is still in L2 when the kernel ends",
-                     "kernel": "gemm_ws2_kernel<*> / gemm_ws_kernel<*> (weight-stationary vocoder resblock convolutions, stages 1-3)", "launches_per_step": ws_n,
-                     "avg_launch_us": ws_ms / max(ws_n, 1) * 1e3, "algorithmic_bytes_per_step": ws_bytes, "peak_source": pk_src,
-                     "tensor_view": {"achieved_tflops": ws_flops / (ws_ms * 1e-3) / 1e12, "frac_of_bf16_sustained": ws_flops / (ws_ms * 1e-3) / 1e12 / peak}},
+        "realtime": realtime,
+        # dominant kernel by work: the vocoder's residual-block convolutions (stages 2-3: one fused launch per residual block,
+        # resblock_fused_kernel; 27 % of the utterance's FLOPs).  Tensor-bound by design: x in / y out are the only HBM traffic.
+        "roofline": {"bound": "tensor", "achieved": fu_flops / max(fu_ms, 1e-9) / 1e9, "peak": peak, "unit": "TFLOP/s",
+                     "frac": fu_flops / max(fu_ms, 1e-9) / 1e9 / peak,
+                     "traffic": 147.3e6, "traffic_note": "dram read+write of one fused launch (ncu --set full, profiles/prof_r2c_rb64_metrics.txt: 98.8 MB read + 48.5 MB written) "
+                                                         "vs 196 MB algorithmic (x in + y out, fp32): part of y is still in the 126 MB L2 when the kernel ends",
+                     "kernel": "resblock_fused_kernel<C, NB, EW, MINB, RES> (one launch per ResBlock1 of vocoder stages 2-3: 6 convolutions, residual stream in TMEM)",
+                     "launches_per_step": fu_n, "avg_launch_us": fu_ms / max(fu_n, 1) * 1e3, "algorithmic_flops_per_step": fu_flops,
+                     "algorithmic_bytes_per_step": fu_bytes, "hbm_view_gbs": fu_bytes / max(fu_ms, 1e-9) / 1e6, "peak_source": pk_src,
+                     "limiter": "shared-memory operand reads of SS-mode tcgen05.mma at N = C_out <= 64 (4 KB of A per M=128,K=16 step: ~46 / 60 cycles per MMA "
+                                "at N = 32 / 64 instead of 16 / 32) and the 64 B/clk TMEM read of the on-chip epilogue steps (RVCB_RB_TRACE, DESIGN.md)"},
+        "roofline_ws": {"bound": "hbm", "achieved": ws_bytes / max(ws_ms, 1e-9) / 1e6, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                        "frac": ws_bytes / max(ws_ms, 1e-9) / 1e6 / pk.get("hbm_gbs"),
+                        "kernel": "gemm_ws2_kernel<*> / gemm_ws_kernel<*> (layer-by-layer weight-stationary convolutions: vocoder stage 1, C = 128)",
+                        "launches_per_step": ws_n, "algorithmic_bytes_per_step": ws_bytes,
+                        "tensor_view": {"achieved_tflops": ws_flops / max(ws_ms, 1e-9) / 1e9, "frac_of_bf16_sustained": ws_flops / max(ws_ms, 1e-9) / 1e9 / peak}},
+        "roofline_vocoder_resblocks": {"bound": "tensor", "achieved": voc_flops / max(voc_ms, 1e-9) / 1e9, "peak": peak, "unit": "TFLOP/s",
+                                       "frac": voc_flops / max(voc_ms, 1e-9) / 1e9 / peak, "ms_per_step": voc_ms,
+                                       "hbm_bytes_per_step": fu_bytes + ws_bytes, "kernel": "fused + weight-stationary families together (stages 1-3)"},
         "roofline_all_gemm": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gemm_tc_kernel<*> + gemm_ws2_kernel<*> + gemm_ws_kernel<*> (all tcgen05 implicit-GEMM launches of one utterance, timed serially)",
+                     "traffic": None, "kernel": "every tcgen05 launch of one utterance (gemm_tc / gemm_sk / gemm_ws* / resblock_fused), timed serially",
                      "launches_per_step": int(gn.value // 3), "ms_per_step": gemm_ms_per_step, "peak_source": pk_src,
                      "algorithmic_flops_per_step": ALGO_FLOPS},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # bounded CPU sample: ONE full utterance through the oracle pipeline on the host cores
+        # (1) e2e through the reference's literal call: wav FILE path in, .index FILE path in (pipeline.py:213-215 re-reads the
+        #     index file on every call; here it is parsed once and cached by (path, mtime)), cache warm
+        import tempfile
+        from scipy.io import wavfile
+        from rvc_b200 import faiss_io
+        with tempfile.TemporaryDirectory() as td:
+            wpath, ipath = os.path.join(td, "utt.wav"), os.path.join(td, "added_IVF2564_Flat_nprobe_1_bench_v2.index")
+            wavfile.write(wpath, 16000, audio.astype(np.float32))
+            faiss_io.write_index(ipath, lay)
+            def file_step():
+                info, out = vc.vc_single(0, wpath, 0, None, "rmvpe", ipath, "", 0.75, 3, 0, 0.25, 0.33)
+                assert out is not None, info
+            for _ in range(3):
+                file_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                file_step()
+            line["e2e"]["file_paths_ms_per_step"] = (time.perf_counter() - t0) / 5 * 1e3
+            line["e2e"]["file_paths_note"] = "vc_single(sid, wav path, ..., .index path): wav decode + the same body + int16 out, index cache warm"
+        # (2) CPU baseline: ONE FULL utterance through the oracle pipeline on the host cores (threads by sweep, warm), and the
+        #     self-check: the product path with the oracle's pitch track and noise draws against that very waveform
         from oracle import ivf as OI
-        cpu_threads = min(os.cpu_count(), 16)
-        torch.set_num_threads(cpu_threads)
-        class _L:  # reuse the already built layout for the oracle index (membership is data, not arithmetic)
-            pass
         assign = np.empty(lay.vectors.shape[0], dtype=np.int64)
         for l in range(len(lay.list_off) - 1):
             assign[lay.list_ids[lay.list_off[l]:lay.list_off[l + 1]]] = l
         oidx = OI.IVFFlat(lay.centroids, lay.vectors, assign)
-        step, credit = make_cpu_sample(audio, oidx)
+        cpipe = make_cpu_pipeline()
+        cpu_threads, sweep = pick_cpu_threads(cpipe, audio, oidx)
         t0 = time.perf_counter()
-        step()
+        ref = cpu_full_step(cpipe, audio, oidx)
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": credit / dt, "unit": "samples/s", "cores": cpu_threads, "kind": "port",
-                                "sample": f"one {CPU_SAMPLE_SECONDS:g} s slice (of 16 s) of the padded utterance through the whole reference path, credited "
-                                          f"{credit:.0f} output samples; torch CPU fp32, {cpu_threads} threads of {os.cpu_count()} cores, no warm-up"}
+        line["cpu_baseline"] = {"value": OUT_SAMPLES / dt, "unit": "samples/s", "cores": cpu_threads, "kind": "port",
+                                "sample": f"ONE FULL utterance (16 s of model compute, {OUT_SAMPLES} output samples) through the whole reference path, after a "
+                                          f"warm-up slice; torch CPU fp32, {cpu_threads} threads of {os.cpu_count()} cores (sweep, s per 1.5 s slice: {sweep}); "
+                                          "IVF search by the oracle's exact lane-order scan (the --impl reference arm uses BLAS)"}
+        tap = cpipe.taps[0]
+        vc.net_g.set_noise(*tap["noise"])
+        got = pipe.pipeline(vc.hubert_model, vc.net_g, 0, audio.copy(), [0, 0, 0], 0, (cpipe.pitch[0].numpy(), cpipe.pitchf[0].numpy().astype(np.float64)),
+                            index, 0.75, 2, 3, 48000, 0, 0.25, "v2", 0.33)
+        err = float(np.abs(got - ref).max() / 32768.0)
+        line["parity_check"] = {"max_abs_err_fullscale": err, "bound": 1.5e-3, "ok": bool(err <= 1.5e-3), "samples": int(ref.shape[0]),
+                                "what": "Pipeline.pipeline on the bench utterance with the oracle's pitch track + noise draws vs the fp32 CPU oracle waveform "
+                                        "(north_star 1e-3; the reference's own fp16 GPU path measures 2.0e-3, profiles/r2a_parity_config2.json)"}
+        assert err <= 1.5e-3, f"bench self-check failed: end-to-end max abs err {err}"
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

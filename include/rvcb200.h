@@ -107,6 +107,17 @@ int rvcb_reflect_pad(const float* d_x, int64_t n, int64_t pad, float* d_out, voi
 /* (int16) x with C truncation, the .astype(np.int16) of modules.py:181: d_out i16[n] */
 int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream);
 
+/* ---- realtime tail of gui.py's audio callback, per block, on the device (gui.py:1024-1087) ---------------------------
+ * replaces: the volume-envelope mix (librosa.feature.rms(frame 4*zc, hop zc) of input and output, align_corners interpolation,
+ * (rms1 / max(rms2, 1e-3)) ^ (1 - rms_mix_rate), gui.py:1024-1056; skipped when rms_mix_rate >= 1) and the SOLA step (normalised
+ * correlation of the block head with the previous tail, arg-max offset, sin^2 cross-fade, buffer update; gui.py:1057-1087, the
+ * use_pv = False branch).  d_infer f32[n], n >= block_frame + sola_buffer_frame + sola_search_frame (scaled in place by the mix);
+ * d_input f32[>= n]: input window from extra_frame on, at the output rate (nullable when rms_mix_rate >= 1); d_sola_buffer
+ * f32[sola_buffer_frame]: state, in/out; d_out f32[block_frame]; d_scratch: >= 2*(n/zc + 1) + sola_search_frame + 1 floats;
+ * d_offset (nullable) i32[1]: the chosen offset. */
+int rvcb_rt_tail(float* d_infer, int n, const float* d_input, int zc, float rms_mix_rate, float* d_sola_buffer, int block_frame,
+                 int sola_buffer_frame, int sola_search_frame, float* d_out, float* d_scratch, int* d_offset, void* stream);
+
 /* ---- f0 post-processing on the device (no host round trip between RMVPE and the synthesizer) ----
  * replaces: F0Predictor._resize_f0 + _interpolate_f0 (rvc/f0/f0.py:31-78) and post_process (rvc/f0/gen.py:10-41, without
  * a manual f0 curve), float64 with numpy's operation order.  d_f0 f32[n_frames] (Hz, 0 = unvoiced) -> d_pitch i64[p_len]
@@ -161,7 +172,7 @@ int rvcb_op_gemm(const rvcb_gemm_desc* d, int impl, void* stream);
 /* ---- op-level entry for the unit tests: the fused residual block of the vocoder -------------
  * replaces: ResBlock1.forward (rvc/layers/residuals.py:68-85): for d in dil: x = x + c2(lrelu(c1_d(lrelu(x, 0.1)), 0.1)).
  * Host weights w1[i], w2[i]: f32 [C, C, k] (weight-norm folded), b1[i], b2[i]: f32 [C]; i = 0..2.  d_x f32 [T, C] (channels last);
- * d_y f32 [rvcb_op_resblock1_out_rows(...), C] (the kernel stores whole tiles; rows >= T are scratch).  C in {32, 64, 128}. */
+ * d_y f32 [T, C].  rvcb_op_resblock1_out_rows returns T when (C, k, dil) has a fused variant (C in {32, 64}), else -1. */
 int64_t rvcb_op_resblock1_out_rows(int C, int k, const int* dil, int T);
 int rvcb_op_resblock1(int C, int k, const int* dil, const float* const* w1, const float* const* b1, const float* const* w2,
                       const float* const* b2, const float* d_x, int T, float* d_y, void* stream);

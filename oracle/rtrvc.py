@@ -1,0 +1,120 @@
+"""Oracle: the realtime engine ``infer.lib.rtrvc.RVC.infer`` and the per-block tail of gui.py's audio callback, fp32 CPU.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Reference sites restated:
+  RVC.__init__ state (pitch ring of 1024 frames)       infer/lib/rtrvc.py:63-66
+  RVC.infer                                            infer/lib/rtrvc.py:134-260
+      last HuBERT frame duplicated                        :163
+      retrieval on frames >= skip_head // 2 only, skipped when any index is -1   :167-187
+      RMVPE on the last f0_extractor_frame samples, pitch ring roll + ``pitch[3:-1]`` write   :199-217
+      x2 nearest upsample, protect mix, net_g.infer(skip_head, return_length, return_length2)   :219-250
+  gui.py audio callback tail (per block, on ``infer_wav``):
+      volume-envelope mix  (librosa.feature.rms(frame 4*zc, hop zc), align_corners interpolation)   gui.py:1024-1056
+      SOLA offset search + cross-fade + buffer update                                             gui.py:1057-1087
+  fade windows sin^2                                   gui.py:841-855
+librosa.feature.rms is restated (centred frames, zero padding) as in oracle/pipeline.py; TorchGate noise reduction
+(gui.py:1015-1023, off by default) and the phase-vocoder cross-fade (use_pv, off by default) are not restated.
+The formant-shift resampling branch (rtrvc.py:251-260, torchaudio Resample) is outside the oracle: tests use formant = 0.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import hubert as OH, ivf as OI, rmvpe as ORM, synth as OS
+from .pipeline import rms_frames
+
+
+class OracleRVC:
+    def __init__(self, hubert_w, rmvpe_w, synth_w, synth_config, index: Optional[OI.IVFFlat], index_rate: float, key: float = 0,
+                 version: str = "v2", noise_seed: int = 0):
+        self.hw, self.rw, self.sw, self.cfg = hubert_w, rmvpe_w, synth_w, synth_config
+        self.index, self.index_rate, self.f0_up_key, self.version = index, index_rate, key, version
+        self.big_npy = index.reconstruct_n(0, index.ntotal) if index is not None else None
+        self.window = 160
+        self.tgt_sr = synth_config[-1] if not isinstance(synth_config[-1], str) else 48000
+        self.cache_pitch = torch.zeros(1024, dtype=torch.long)
+        self.cache_pitchf = torch.zeros(1024, dtype=torch.float32)
+        self.gen = torch.Generator().manual_seed(noise_seed)
+        self.taps = []
+
+    @torch.no_grad()
+    def infer(self, input_wav: np.ndarray, block_frame_16k: int, skip_head: int, return_length: int, protect: float = 1.0):
+        wav = torch.from_numpy(np.asarray(input_wav, dtype=np.float32))
+        feats = OH.extract_features(self.hw, wav.view(1, -1), 9 if self.version == "v1" else 12)
+        if self.version == "v1":
+            feats = OH.final_proj(self.hw, feats)
+        feats = torch.cat((feats, feats[:, -1:, :]), 1)                                     # rtrvc.py:163
+        tap = {"feats_hubert": feats.clone()}
+        if self.index is not None and self.index_rate > 0:
+            npy = feats[0][skip_head // 2:].numpy()
+            score, ix = self.index.search(npy, k=8)
+            tap["ix"] = ix
+            if (ix >= 0).all():                                                              # rtrvc.py:173
+                npy = OI.blend(npy, score, ix, self.big_npy, self.index_rate)
+                feats[0][skip_head // 2:] = torch.from_numpy(npy)
+        p_len = wav.shape[0] // self.window
+        return_length2 = return_length                                                       # formant shift 0
+        f0_extractor_frame = block_frame_16k + 800
+        f0_extractor_frame = 5120 * ((f0_extractor_frame - 1) // 5120 + 1) - self.window     # rtrvc.py:199-203
+        pitch, pitchf = ORM.calculate(self.rw, wav[-f0_extractor_frame:].numpy(), None, self.f0_up_key)
+        pitch, pitchf = torch.from_numpy(pitch.astype(np.int64)), torch.from_numpy(pitchf.astype(np.float32))
+        shift = block_frame_16k // self.window
+        self.cache_pitch[:-shift] = self.cache_pitch[shift:].clone()
+        self.cache_pitchf[:-shift] = self.cache_pitchf[shift:].clone()
+        self.cache_pitch[4 - pitch.shape[0]:] = pitch[3:-1]
+        self.cache_pitchf[4 - pitch.shape[0]:] = pitchf[3:-1]
+        cache_pitch = self.cache_pitch[None, -p_len:]
+        cache_pitchf = self.cache_pitchf[None, -p_len:] * return_length2 / return_length
+        feats = F.interpolate(feats.permute(0, 2, 1), scale_factor=2).permute(0, 2, 1)[:, :p_len, :]
+        upp = self.tgt_sr // 100
+        flow_head = max(skip_head - 24, 0)
+        n1 = torch.randn(1, self.cfg[2], p_len - flow_head, generator=self.gen)
+        n2 = torch.randn(1, return_length * upp, 1, generator=self.gen)
+        tap.update(phone=feats.clone(), noise=(n1, n2), pitch=cache_pitch.clone(), pitchf=cache_pitchf.clone())
+        self.taps.append(tap)
+        out = OS.synth_infer(self.sw, self.cfg, feats, torch.tensor([p_len]), torch.tensor([0]), cache_pitch, cache_pitchf, n1, n2,
+                             skip_head=skip_head, return_length=return_length, return_length2=return_length2)
+        return out[0, 0].numpy()
+
+
+def fade_windows(n: int):
+    """gui.py:841-855"""
+    fade_in = torch.sin(0.5 * np.pi * torch.linspace(0.0, 1.0, steps=n, dtype=torch.float32)) ** 2
+    return fade_in, 1 - fade_in
+
+
+def envelope_mix(infer_wav: torch.Tensor, input_wav: torch.Tensor, zc: int, rms_mix_rate: float) -> torch.Tensor:
+    """gui.py:1024-1056 (returns a new tensor; the reference scales ``infer_wav`` in place)."""
+    n = infer_wav.shape[0]
+    rms1 = torch.from_numpy(rms_frames(input_wav[:n].numpy(), 4 * zc, zc))
+    rms1 = F.interpolate(rms1.unsqueeze(0), size=n + 1, mode="linear", align_corners=True)[0, 0, :-1]
+    rms2 = torch.from_numpy(rms_frames(infer_wav.numpy(), 4 * zc, zc))
+    rms2 = F.interpolate(rms2.unsqueeze(0), size=n + 1, mode="linear", align_corners=True)[0, 0, :-1]
+    rms2 = torch.max(rms2, torch.zeros_like(rms2) + 1e-3)
+    return infer_wav * torch.pow(rms1 / rms2, torch.tensor(1 - rms_mix_rate))
+
+
+class SolaTail:
+    """State + per-block step of gui.py:1057-1087 (SOLA from DDSP-SVC), without the phase vocoder."""
+
+    def __init__(self, block_frame: int, sola_buffer_frame: int, sola_search_frame: int):
+        self.block_frame, self.sola_buffer_frame, self.sola_search_frame = block_frame, sola_buffer_frame, sola_search_frame
+        self.sola_buffer = torch.zeros(sola_buffer_frame)
+        self.fade_in, self.fade_out = fade_windows(sola_buffer_frame)
+
+    def step(self, infer_wav: torch.Tensor):
+        infer_wav = infer_wav.clone()
+        conv_input = infer_wav[None, None, : self.sola_buffer_frame + self.sola_search_frame]
+        cor_nom = F.conv1d(conv_input, self.sola_buffer[None, None, :])
+        cor_den = torch.sqrt(F.conv1d(conv_input ** 2, torch.ones(1, 1, self.sola_buffer_frame)) + 1e-8)
+        sola_offset = int(torch.argmax(cor_nom[0, 0] / cor_den[0, 0]))
+        infer_wav = infer_wav[sola_offset:]
+        infer_wav[: self.sola_buffer_frame] *= self.fade_in
+        infer_wav[: self.sola_buffer_frame] += self.sola_buffer * self.fade_out
+        self.sola_buffer[:] = infer_wav[self.block_frame: self.block_frame + self.sola_buffer_frame]
+        return infer_wav[: self.block_frame].clone(), sola_offset

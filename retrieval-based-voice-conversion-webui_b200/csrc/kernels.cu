@@ -933,3 +933,137 @@ void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double
 }
 
 }  // namespace rvcb
+
+// =====================================================================================================================
+// Realtime tail of gui.py's audio callback, per block, on the device (gui.py:1024-1087): volume-envelope mix
+// (librosa.feature.rms(frame 4*zc, hop zc) of the input and of the converted block, align_corners linear interpolation,
+// power-law mix) and SOLA (normalised cross-correlation of the block head with the previous block's tail, arg-max offset,
+// sin^2 cross-fade, buffer update).
+// =====================================================================================================================
+namespace rvcb {
+
+__global__ void rt_rms_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int frame, int hop, int nf, float* __restrict__ rms) {
+    const int sig = blockIdx.x / nf, f = blockIdx.x % nf;
+    const float* y = sig ? b : a;
+    const int lo = max(f * hop - frame / 2, 0), hi = min(f * hop - frame / 2 + frame, n);     // centred frame, zero padding
+    float s = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s += y[i] * y[i];
+    __shared__ float sh[32];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) rms[sig * nf + f] = sqrtf(s / (float)frame);
+    }
+}
+
+// F.interpolate(rms[None], size = n + 1, mode = "linear", align_corners = True)[0, 0, :-1], then y *= (r1 / max(r2, 1e-3)) ^ (1 - rate)
+__global__ void rt_mix_kernel(float* __restrict__ y, int n, const float* __restrict__ rms, int nf, float expo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float scale = (float)(nf - 1) / (float)n;
+    const float src = scale * (float)i;
+    const int i0 = (int)src, i1 = min(i0 + 1, nf - 1);
+    const float l1 = src - (float)i0, l0 = 1.f - l1;
+    const float r1 = l0 * rms[i0] + l1 * rms[i1];
+    const float r2 = fmaxf(l0 * rms[nf + i0] + l1 * rms[nf + i1], 1e-3f);
+    y[i] *= powf(r1 / r2, expo);
+}
+
+__global__ void sola_corr_kernel(const float* __restrict__ y, const float* __restrict__ buf, int nbuf, float* __restrict__ score) {
+    const int o = blockIdx.x;
+    float nom = 0.f, den = 0.f;
+    for (int i = threadIdx.x; i < nbuf; i += blockDim.x) {
+        const float v = y[o + i];
+        nom += v * buf[i];
+        den += v * v;
+    }
+    __shared__ float sh[2][32];
+    for (int k = 16; k; k >>= 1) { nom += __shfl_xor_sync(0xffffffffu, nom, k); den += __shfl_xor_sync(0xffffffffu, den, k); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = nom; sh[1][threadIdx.x >> 5] = den; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        nom = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.f;
+        den = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.f;
+        for (int k = 16; k; k >>= 1) { nom += __shfl_xor_sync(0xffffffffu, nom, k); den += __shfl_xor_sync(0xffffffffu, den, k); }
+        if (threadIdx.x == 0) score[o] = nom / sqrtf(den + 1e-8f);
+    }
+}
+
+__device__ __forceinline__ float sola_fade_in(int i, int n) {      // sin(0.5*pi*linspace(0, 1, n))^2, torch's float32 linspace
+    if (n <= 1) return 0.f;
+    const float step = 1.f / (float)(n - 1);
+    const float t = i < n / 2 ? (float)i * step : 1.f - (float)(n - 1 - i) * step;
+    const float s = sinf(1.5707963267948966f * t);
+    return s * s;
+}
+
+// one block: arg-max of the scores (first maximum), cross-fade, output block, new SOLA buffer
+__global__ void sola_finish_kernel(const float* __restrict__ y, const float* __restrict__ score, int nscore, float* __restrict__ buf, int nbuf,
+                                   int block, float* __restrict__ out, int* __restrict__ offset_out) {
+    extern __shared__ float newbuf[];
+    __shared__ float bv[32];
+    __shared__ int bi[32], off_s;
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < nscore; i += blockDim.x) {
+        const float v = score[i];
+        if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+    for (int k = 16; k; k >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, k);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, k);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? bv[threadIdx.x] : -INFINITY;
+        idx = threadIdx.x < (blockDim.x >> 5) ? bi[threadIdx.x] : 0x7fffffff;
+        for (int k = 16; k; k >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, k);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, k);
+            if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+        }
+        if (threadIdx.x == 0) {
+            off_s = idx == 0x7fffffff ? 0 : idx;
+            if (offset_out) *offset_out = off_s;
+        }
+    }
+    __syncthreads();
+    const int off = off_s;
+    auto faded = [&](int i) {          // element i of infer_wav[off:] after the in-place cross-fade of its first nbuf samples
+        float v = y[off + i];
+        if (i < nbuf) {
+            const float fi = sola_fade_in(i, nbuf);
+            v = v * fi + buf[i] * (1.f - fi);
+        }
+        return v;
+    };
+    for (int i = threadIdx.x; i < nbuf; i += blockDim.x) newbuf[i] = faded(block + i);
+    for (int i = threadIdx.x; i < block; i += blockDim.x) out[i] = faded(i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbuf; i += blockDim.x) buf[i] = newbuf[i];
+}
+
+void rt_tail(float* infer, int n, const float* input, int zc, float rms_mix_rate, float* sola_buffer, int block_frame, int nbuf, int nsearch,
+             float* out, float* scratch, int* offset, cudaStream_t s) {
+    RVCB_CHECK(n >= block_frame + nbuf + nsearch && nbuf >= 1 && nbuf <= 8192 && zc >= 1, "rt_tail: bad sizes");
+    const int nf = 1 + n / zc;
+    float* rms = scratch;                       // [2, nf]
+    float* score = scratch + 2 * nf;            // [nsearch + 1]
+    if (rms_mix_rate < 1.f) {
+        RVCB_CHECK(input != nullptr, "rt_tail: the envelope mix needs the input window");
+        rt_rms_kernel<<<2 * nf, 256, 0, s>>>(input, infer, n, 4 * zc, zc, nf, rms);
+        rt_mix_kernel<<<ceil_div(n, 256), 256, 0, s>>>(infer, n, rms, nf, 1.f - rms_mix_rate);
+        count_launch(2);
+    }
+    sola_corr_kernel<<<nsearch + 1, 256, 0, s>>>(infer, sola_buffer, nbuf, score);
+    sola_finish_kernel<<<1, 1024, nbuf * sizeof(float), s>>>(infer, score, nsearch + 1, sola_buffer, nbuf, block_frame, out, offset);
+    KERNEL_CHECK();
+    count_launch(2);
+}
+
+}  // namespace rvcb

@@ -68,4 +68,9 @@ void f32_to_i16(const float* x, long n, short* out, cudaStream_t s);
 void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double f0_min, double f0_max, long long* pitch, float* pitchf,
              double* scratch, cudaStream_t s);
 
+// Realtime tail of gui.py's audio callback on the device (gui.py:1024-1087): envelope mix (rms_mix_rate < 1, in place on
+// `infer`) + SOLA offset search, cross-fade, output block and buffer update.  scratch: >= 2 * (n / zc + 1) + nsearch + 1 floats.
+void rt_tail(float* infer, int n, const float* input, int zc, float rms_mix_rate, float* sola_buffer, int block_frame, int nbuf, int nsearch,
+             float* out, float* scratch, int* offset, cudaStream_t s);
+
 }  // namespace rvcb

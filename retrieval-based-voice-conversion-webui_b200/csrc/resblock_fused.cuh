@@ -19,10 +19,10 @@ struct RBFusedWeights {
 RBFusedWeights pack_resblock_fused(DevOwner& own, int C, int k, const int* dil, const float* const* w1, const float* const* b1,
                                    const float* const* w2, const float* const* b2);
 bool resblock_fused_supported(int C, int k, const int* dil);
-// rows the output buffer must hold: the last tile is stored whole (ceil(T / R) * R >= T rows)
+// rows the output buffer must hold (= T; -1 if the configuration has no fused variant)
 long resblock_fused_out_rows(int C, int k, const int* dil, int T);
 int resblock_fused_tile_rows(int C);
-// y[0:T, :] = ResBlock1(x[0:T, :]);  x, y fp32 [rows, C] dense (ld = C), y with resblock_fused_out_rows rows
+// y[0:T, :] = ResBlock1(x[0:T, :]);  x, y fp32 [rows, C] dense (ld = C), y with T rows
 void resblock_fused(const RBFusedWeights& w, const float* x, float* y, int T, cudaStream_t stream);
 // out[t, c] = (half) lrelu((y[0] + .. + y[nk-1])[t, c] / nk, slope), out row stride ld
 void resblock_mean_lrelu(const float* const* y, int nk, long T, int C, __half* out, long ld, float slope, cudaStream_t stream);

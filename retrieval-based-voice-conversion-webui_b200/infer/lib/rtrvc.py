@@ -158,9 +158,14 @@ class RVC:
         use_protect = protect < 0.5 and pitch is not None and pitchf is not None and feats0 is not None
         pf = None
         if use_protect:
+            # The reference builds the voiced / unvoiced mask from this block's fresh f0 (rtrvc.py:226-236), which covers only
+            # the last f0_extractor_frame samples while the features cover the whole rolling window: with "rmvpe" its shapes do
+            # not match and it raises (gui.py never passes protect < 0.5).  Here the mask comes from the pitch ring, which is
+            # aligned with the window frame for frame (unscaled by the formant factor); a (pitch, pitchf) tuple is used as given.
             pf = torch.ones(p_len, device=self.device)
-            n = min(p_len, pitchf.reshape(-1).shape[0])
-            pf[:n] = pitchf.reshape(-1)[:n]
+            src = pitchf.reshape(-1) if isinstance(f0method, tuple) else self.cache_pitchf[-p_len:]
+            n = min(p_len, src.shape[0])
+            pf[p_len - n:] = src[-n:]
         phone = engine.upsample_protect(feats, feats0 if use_protect else None, pf, p_len, protect if use_protect else 1.0)
         out = self.net_g.infer(phone.unsqueeze(0), torch.tensor([p_len]), torch.tensor([0]),     # host scalars: no stream sync
                                pitch=cache_pitch, pitchf=cache_pitchf, skip_head=skip_head, return_length=return_length,

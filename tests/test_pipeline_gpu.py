@@ -55,7 +55,7 @@ def test_pipeline_matches_oracle_with_shared_pitch_and_noise():
     assert same >= 0.98, same
     err = np.abs(out - ref).max() / 32768.0
     print(f"[parity] 2 s utterance: all-8 neighbours same {same:.4f}, e2e max abs err {err:.3e}")
-    assert err < 2e-3, f"end-to-end max abs err (full scale) {err}"
+    assert err < 1.5e-3, f"end-to-end max abs err (full scale) {err}"      # measured 7.4e-4
     # 2) the full path with its own RMVPE f0: coarse pitch agrees on >= 95 % of frames, f0 within 1 % where both voiced
     c2, f2 = pipe.f0_gen.calculate(np.pad(__import__("scipy.signal").signal.filtfilt(
         __import__("infer.modules.vc.pipeline", fromlist=["bh"]).bh, __import__("infer.modules.vc.pipeline", fromlist=["ah"]).ah, audio),
@@ -146,7 +146,7 @@ def test_pipeline_multichunk_long_audio_matches_oracle():
     assert out.shape == ref.shape
     err = np.abs(out - ref).max() / 32768.0
     print(f"[parity] multi-chunk 7 s utterance: e2e max abs err {err:.3e}")
-    assert err < 2e-3, err
+    assert err < 1.5e-3, err      # measured 4.9e-4
 
 
 def test_vc_single_with_index_file_and_vc_multi(tmp_path):

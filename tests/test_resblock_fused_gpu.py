@@ -33,7 +33,7 @@ def _run(Cc, k, dil, T, seed):
     b2 = [torch.randn(Cc, generator=g) * 0.1 for _ in range(3)]
     dil_a = (C.c_int * 3)(*dil)
     rows = _lib.lib().rvcb_op_resblock1_out_rows(Cc, k, dil_a, T)
-    assert rows >= T
+    assert rows == T
     xd = x.cuda()
     yd = torch.full((rows, Cc), float("nan"), device="cuda")
     arr = lambda ts: (C.c_void_p * 3)(*[t.data_ptr() for t in ts])
@@ -57,7 +57,7 @@ def _run(Cc, k, dil, T, seed):
 
 
 @pytest.mark.parametrize("Cc,k,T", [(32, 3, 5000), (32, 11, 2000), (32, 7, 150000), (64, 7, 3000), (64, 11, 700), (64, 3, 90000),
-                                    (128, 3, 1000), (128, 7, 900), (128, 11, 40000)])
+                                    (64, 11, 40000), (32, 11, 100000)])
 def test_fused_resblock_matches_torch(Cc, k, T):
     _run(Cc, k, (1, 3, 5), T, seed=Cc * 100 + k)
 
