@@ -321,3 +321,97 @@ def test_faiss_container_reader_variants(tmp_path):
     p.write_bytes(build(metric=0))
     with pytest.raises(ValueError, match="METRIC_L2"):
         faiss_io.read_index(str(p))
+
+
+def test_train_index_file_protocol_and_minibatch_kmeans_branch(tmp_path):
+    """rvc_b200.index_build.train_index vs web.py:499-596: feature files -> shuffled total_fea.npy, n_ivf formula, trained_ / added_
+    index files in the IwFl container (read back by the faiss-free reader), the MiniBatchKMeans branch above the row threshold."""
+    from rvc_b200 import faiss_io, index_build
+    logs = tmp_path / "logs"
+    fdir = logs / "exp1" / "3_feature768"
+    fdir.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    parts = [rng.standard_normal((n, 768)).astype(np.float32) * 0.2 for n in (700, 900, 400)]
+    for i, p in enumerate(parts):
+        np.save(fdir / f"u{i}.npy", p)
+    out_root = tmp_path / "outside"
+    out_root.mkdir()
+    np.random.seed(3)
+    msgs = list(index_build.train_index("exp1", "v2", logs_root=str(logs), outside_index_root=str(out_root), device="cpu"))
+    n, n_ivf = 2000, min(int(16 * np.sqrt(2000)), 2000 // 39)
+    assert f"({n}, 768),{n_ivf}" in msgs[-1] and "training" in msgs[-1] and "adding" in msgs[-1] and "Successfully built index into" in msgs[-1]
+    exp = logs / "exp1"
+    total = np.load(exp / "total_fea.npy")
+    np.random.seed(3)
+    idx = np.arange(n); np.random.shuffle(idx)
+    assert np.array_equal(total, np.concatenate(parts, 0)[idx])                     # web.py:517-520, 543
+    added = exp / f"added_IVF{n_ivf}_Flat_nprobe_1_exp1_v2.index"
+    trained = exp / f"trained_IVF{n_ivf}_Flat_nprobe_1_exp1_v2.index"
+    assert added.exists() and trained.exists()
+    lay = faiss_io.read_index(str(added))
+    assert lay.centroids.shape == (n_ivf, 768) and np.array_equal(lay.vectors, total)      # reconstruct_n(0, ntotal) == total_fea (add order)
+    assert sorted(lay.list_ids.tolist()) == list(range(n)) and lay.list_off[-1] == n
+    # every vector sits in the list of its nearest centroid
+    d = ((total[:, None, :] - lay.centroids[None, :, :]) ** 2).sum(-1)
+    assign = np.empty(n, np.int64)
+    for l in range(n_ivf):
+        assign[lay.list_ids[lay.list_off[l]:lay.list_off[l + 1]]] = l
+    assert (d[np.arange(n), assign] <= d.min(1) * (1 + 1e-5) + 1e-6).all()
+    empty = faiss_io.read_index(str(trained))
+    assert empty.ntotal == 0 and np.array_equal(empty.centroids, lay.centroids)
+    assert (out_root / f"exp1_IVF{n_ivf}_Flat_nprobe_1_exp1_v2.index").exists()
+    # the > 2e5-rows branch (threshold lowered): features are replaced by MiniBatchKMeans centres
+    msgs = list(index_build.train_index("exp1", "v2", logs_root=str(logs), device="cpu", kmeans_threshold=1000, kmeans_clusters=300))
+    assert "Trying doing kmeans 2000 shape to 10k centers." in msgs[0]
+    assert np.load(exp / "total_fea.npy").shape == (300, 768)
+    assert list(index_build.train_index("missing", "v2", logs_root=str(logs)))[0].startswith("请先进行特征提取")
+
+
+def test_index_reader_rejects_inconsistent_files(tmp_path):
+    from oracle import ivf as OI, weights as OW
+    from rvc_b200 import faiss_io
+    idx = OI.build_ivf(OW.index_vectors(300, 768, 1).numpy(), 8, seed=0, exact_assign=True)
+    path = str(tmp_path / "a.index")
+    faiss_io.write_index(path, idx)
+    good = open(path, "rb").read()
+    assert faiss_io.read_index(path).ntotal == 300
+    import struct
+    bad = bytearray(good)
+    struct.pack_into("<q", bad, 4 + 4, 301)                          # ntotal in the header no longer matches the list sizes
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        faiss_io.read_index(path)
+    bad = bytearray(good)
+    struct.pack_into("<Q", bad, 4 + 33 + 8, 4)                       # nprobe != 1
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        faiss_io.read_index(path)
+    bad = bytearray(good)
+    struct.pack_into("<q", bad, len(bad) - 8, 10 ** 6)               # last vector id out of range
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        faiss_io.read_index(path)
+
+
+def test_checkpoint_unpickler_is_an_allowlist(tmp_path):
+    """infer/modules/vc/utils.py: a crafted hubert_base.pt must not be able to import callables (os.system, eval, ...)."""
+    import argparse
+    import collections
+    from infer.modules.vc import utils as U
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("touch %s" % (tmp_path / "pwned"),))
+    sd = collections.OrderedDict(a=torch.randn(3, 4).half(), b=torch.nn.Parameter(torch.randn(2)))
+    torch.save({"model": sd, "cfg": argparse.Namespace(x=1), "evil": Evil(), "np": np.arange(3)}, tmp_path / "ck.pt")
+    out = U._load_fairseq_state_dict(str(tmp_path / "ck.pt"))
+    assert set(out) == {"a", "b"} and out["a"].dtype == torch.float16 and not (tmp_path / "pwned").exists()
+
+
+def test_mel_filterbank_matches_torchaudio_htk_slaney():
+    """oracle/rmvpe.py mel_filterbank restates librosa.filters.mel(sr=16000, n_fft=1024, n_mels=128, fmin=30, fmax=8000, htk=True)
+    (rvc/f0/mel.py:27-34; librosa is not installed): independent check against torchaudio's HTK / slaney-normalised bank."""
+    torchaudio = pytest.importorskip("torchaudio")
+    from oracle import rmvpe as ORM
+    fb = torchaudio.functional.melscale_fbanks(513, 30.0, 8000.0, 128, 16000, norm="slaney", mel_scale="htk").t().numpy()
+    assert np.abs(ORM.mel_filterbank() - fb).max() < 1e-6
