@@ -23,6 +23,7 @@ extern "C" {
 typedef struct rvcb_weights rvcb_weights;
 typedef struct rvcb_hubert rvcb_hubert;
 typedef struct rvcb_index rvcb_index;
+typedef struct rvcb_flat rvcb_flat;
 typedef struct rvcb_rmvpe rvcb_rmvpe;
 typedef struct rvcb_synth rvcb_synth;
 
@@ -31,6 +32,9 @@ int rvcb_init(int device);                 /* cudaSetDevice + capability check (
 const char* rvcb_last_error(void);
 unsigned long long rvcb_launch_count(void); /* kernels launched by this library so far */
 const char* rvcb_version(void);
+/* Cap the CTAs of the persistent GEMM / kNN grids launched from now on (0 = every SM); returns the previous cap.  Process-wide
+ * launch-time setting: the front doors use it to run the two independent front branches side by side on disjoint SMs. */
+int rvcb_set_grid_cap(int max_ctas);
 
 /* per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py roofline); begin resets, end syncs and sums */
 int rvcb_prof_begin(void);
@@ -76,6 +80,13 @@ int rvcb_index_blend(rvcb_index* ix, const float* d_feats_in, int nq, int k, con
 int rvcb_knn_bruteforce_top1(const float* d_db, int64_t n, int d, const float* d_q, int nq, float* d_D,
                              int64_t* d_I, void* stream);
 void rvcb_index_destroy(rvcb_index* ix);
+/* exact brute-force L2 top-1 for query BATCHES (BASELINE config #5 at nq >= 32): the handle keeps an fp16 mirror of d_db (which
+ * must stay alive) and ||v||^2; scores come from the tcgen05 GEMM engine, the 32 best candidates per query are re-ranked with
+ * the exact fp32 lane-order distance and a rounding-error certificate sends any doubtful query to the exact scan, so d_D / d_I
+ * are bit-identical to rvcb_knn_bruteforce_top1.  RVCB_KNN_TC=0 forces the scan. */
+int rvcb_flat_create(const float* d_db, int64_t n, int d, rvcb_flat** out);
+int rvcb_flat_search_top1(rvcb_flat* f, const float* d_q, int nq, float* d_D, int64_t* d_I, void* stream);
+void rvcb_flat_destroy(rvcb_flat* f);
 
 /* ---- retrieval epilogue: x2 nearest upsample + protect mix (pipeline.py:140-160) ----------- */
 /* d_feats f32[T_h,C], d_feats0 (nullable) f32[T_h,C], d_pitchf (nullable) f32[T]; out f32[T,C], T <= 2*T_h */

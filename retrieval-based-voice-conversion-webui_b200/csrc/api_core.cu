@@ -7,6 +7,7 @@
 
 namespace rvcb {
 unsigned long long g_launch_count = 0;
+int g_grid_cap = 0;
 static thread_local std::string g_err;
 void set_last_error(const std::string& s) { g_err = s; }
 }  // namespace rvcb
@@ -18,6 +19,11 @@ extern "C" {
 
 const char* rvcb_last_error(void) { return rvcb::g_err.c_str(); }
 unsigned long long rvcb_launch_count(void) { return rvcb::g_launch_count; }
+int rvcb_set_grid_cap(int max_ctas) {
+    const int prev = rvcb::g_grid_cap;
+    rvcb::g_grid_cap = max_ctas > 0 ? max_ctas : 0;
+    return prev;
+}
 const char* rvcb_version(void) { return "rvcb200 0.1 (sm_100a)"; }
 
 int rvcb_init(int device) {

@@ -38,6 +38,11 @@ struct Error : std::runtime_error {
 // launch counter (bench.py reports gpu_launches from it)
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
+// Upper bound on the CTAs of a persistent grid (0 = all SMs).  The Python front doors lower it to half the machine while the two
+// independent front branches (RMVPE on one stream, HuBERT + retrieval on another) are being launched, so that kernels of the two
+// streams run side by side on disjoint SMs instead of taking turns at the whole chip (rvcb_set_grid_cap).
+extern int g_grid_cap;
+inline int sm_budget(int sms) { return (g_grid_cap > 0 && g_grid_cap < sms) ? g_grid_cap : sms; }
 
 enum Act : int {
     ACT_NONE = 0,

@@ -500,7 +500,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
         CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         configured = true;
     }
-    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    const int grid = p.num_tiles < sm_budget(num_sms) ? p.num_tiles : sm_budget(num_sms);
     if (g_prof_on) gemm_prof_record_begin(stream);
     launch_pdl(gemm_tc_kernel<BN, BK, RS>, grid, kThreads, C::SMEM, stream, ta, tb, tr, p);
     KERNEL_CHECK();

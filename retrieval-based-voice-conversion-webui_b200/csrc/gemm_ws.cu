@@ -862,6 +862,7 @@ bool gemm_ws_try(const GemmArgs& g, cudaStream_t stream) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        sms = sm_budget(sms);
     }
     if (ws2_try(g, stream, BK, nkc, rmin, HRp, m_tiles, sms, bo_mode)) return true;
     int BN = 0;

@@ -11,6 +11,7 @@
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
 #include "common.cuh"
+#include "gemm.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -32,10 +33,13 @@ struct rvcb_index {
     unsigned long long* best = nullptr;
     int best_cap = 0;
     std::vector<unsigned long long*> retired;     // outgrown workspaces (see ensure_ws)
+    struct FlatTC* coarse_tc = nullptr;           // fp16 mirror of the centroids for the tensor-core coarse pass (query batches)
     ~rvcb_index() {
         cudaFree(centroids); cudaFree(vectors); cudaFree(list_off); cudaFree(list_ids); cudaFree(best);
         for (auto* p : retired) cudaFree(p);
+        destroy_coarse();
     }
+    void destroy_coarse();
 };
 
 template <int CH>
@@ -56,14 +60,24 @@ __device__ __forceinline__ float lane_order_dist(const float4 (&q)[CH], const fl
 }
 
 // best[q] = min over db rows of pack(dist, idx).  grid = (query tiles, db splits)
+// `active` (nullable): only the flagged queries are searched (a tile without any flagged query returns at once) -- the exact
+// fallback of the tensor-core short-list path below.
 template <int CH>
 __global__ void __launch_bounds__(256) knn_top1_kernel(const float* __restrict__ db, long long n, const float* __restrict__ q, int nq,
-                                                       unsigned long long* __restrict__ best) {
+                                                       unsigned long long* __restrict__ best, const unsigned char* __restrict__ active) {
     extern __shared__ float4 qs[];                 // [QT][d/4]
     constexpr int d = CH * 128;
     constexpr int d4 = d >> 2;
     const int q0 = blockIdx.x * QT;
     const int nq_tile = min(QT, nq - q0);
+    if (active) {
+        __shared__ int any_active;
+        if (threadIdx.x == 0) any_active = 0;
+        __syncthreads();
+        if (threadIdx.x < nq_tile && active[q0 + threadIdx.x]) any_active = 1;
+        __syncthreads();
+        if (!any_active) return;
+    }
     for (int i = threadIdx.x; i < QT * d4; i += blockDim.x) {
         const int qi = i / d4;
         qs[i] = qi < nq_tile ? reinterpret_cast<const float4*>(q + (long)(q0 + qi) * d)[i - qi * d4] : make_float4(0, 0, 0, 0);
@@ -91,7 +105,7 @@ __global__ void __launch_bounds__(256) knn_top1_kernel(const float* __restrict__
             }
         }
     }
-    if (lane < nq_tile && besti != 0xffffffffu) {
+    if (lane < nq_tile && besti != 0xffffffffu && (!active || active[q0 + lane])) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(bestd) << 32) | besti;
         atomicMin(&best[q0 + lane], key);
     }
@@ -195,14 +209,16 @@ __global__ void blend_kernel(const float* __restrict__ vectors, long long ntotal
     }
 }
 
-static void top1(const float* db, long long n, int d, const float* q, int nq, unsigned long long* best, cudaStream_t st) {
+static void top1(const float* db, long long n, int d, const float* q, int nq, unsigned long long* best, cudaStream_t st,
+                 const unsigned char* active = nullptr) {
     RVCB_CHECK(d % 128 == 0 && d <= 1024, "knn: d must be a multiple of 128 and <= 1024");
     RVCB_CHECK(n < 0xffffffffLL, "knn: database too large");
-    CUDA_CHECK(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * nq, st));
+    if (!active) CUDA_CHECK(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * nq, st));
     const int qtiles = ceil_div(nq, QT);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms = sm_budget(sms);
     // enough splits to fill the machine (2 CTAs/SM by shared memory), at least 64 rows per split
     long long splits = (2LL * sms + qtiles - 1) / qtiles;
     const long long max_splits = (n + 63) / 64;
@@ -216,7 +232,7 @@ static void top1(const float* db, long long n, int d, const float* q, int nq, un
             CUDA_CHECK(cudaFuncSetAttribute(knn_top1_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr = true;                                                                                           \
         }                                                                                                          \
-        knn_top1_kernel<CH><<<dim3(qtiles, (unsigned)splits), 256, smem, st>>>(db, n, q, nq, best);                \
+        knn_top1_kernel<CH><<<dim3(qtiles, (unsigned)splits), 256, smem, st>>>(db, n, q, nq, best, active);                \
         break;                                                                                                     \
     }
     switch (d / 128) {
@@ -226,6 +242,216 @@ static void top1(const float* db, long long n, int d, const float* q, int nq, un
 #undef RVCB_TOP1
     KERNEL_CHECK();
     count_launch();
+}
+
+
+// =====================================================================================================================
+// Tensor-core short list for query BATCHES (BASELINE config #5 at nq >= 32, and the 799 x 2564 coarse pass of one utterance).
+// The exact scan above is 3 flops per element of fixed-order SIMT arithmetic: beyond one query tile it is ALU-bound, not
+// HBM-bound.  Here the ranking score  s(q, v) = ||v||^2 - 2 q.v  comes from the tcgen05 implicit-GEMM engine (fp16 operands,
+// fp32 accumulate; the fp16 mirror of the database and ||v||^2 are built once), a warp per query keeps the 32 best-scoring
+// candidates, and those 32 are re-ranked with the EXACT lane-order distance on the fp32 vectors, so D and I stay bit-exact
+// against oracle/ivf.py.  Soundness: the fp16 rounding of q and v moves a score by at most eps = 3 * 2^-10 * ||q|| * max||v||;
+// if the 32nd score does not clear the exact winner by more than eps the query is flagged and searched again by the exact
+// kernel (masked).  Nothing is approximated in what is returned.
+// =====================================================================================================================
+constexpr int TC_K = 32;             // candidates per query
+constexpr int TC_QB = 1024;          // query rows per GEMM
+constexpr int TC_NC = 32768;         // database rows per GEMM
+
+struct FlatTC {
+    const float* db32 = nullptr;
+    long long n = 0;
+    int d = 0;
+    __half* db16 = nullptr;
+    float* vnorm = nullptr;          // [n] ||v||^2 (+ slot n: max ||v||)
+    // workspace, grown geometrically; outgrown blocks stay alive (captured graphs may point at them)
+    __half* q16 = nullptr; float* qn = nullptr; float* cs = nullptr; int* ci = nullptr; unsigned char* flags = nullptr; float* S = nullptr;
+    int q_cap = 0;
+    std::vector<void*> owned;
+    ~FlatTC() { for (void* p : owned) cudaFree(p); cudaFree(db16); cudaFree(vnorm); }
+};
+
+__global__ void tc_prep_db_kernel(const float* __restrict__ db, long long n, int d, __half* __restrict__ db16, float* __restrict__ vnorm) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(db + r * d + c);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(db16 + r * d + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    }
+    for (int s2 = 16; s2; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+    if (lane == 0) {
+        vnorm[r] = acc;
+        atomicMax(reinterpret_cast<int*>(vnorm + n), __float_as_int(sqrtf(acc)));      // positive floats order like ints
+    }
+}
+
+// q16 = half(-2 q); qn = (||q||^2, ||q||); candidates reset
+__global__ void tc_prep_q_kernel(const float* __restrict__ q, int nq, int d, __half* __restrict__ q16, float* __restrict__ qn,
+                                 float* __restrict__ cs, int* __restrict__ ci) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= nq) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(q + (long)r * d + c);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        const __half2 h0 = __floats2half2_rn(-2.f * v.x, -2.f * v.y), h1 = __floats2half2_rn(-2.f * v.z, -2.f * v.w);
+        *reinterpret_cast<uint2*>(q16 + (long)r * d + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    }
+    for (int s2 = 16; s2; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+    if (lane == 0) { qn[2 * r] = acc; qn[2 * r + 1] = sqrtf(acc); }
+    cs[(long)r * TC_K + lane] = INFINITY;
+    ci[(long)r * TC_K + lane] = -1;
+}
+
+// one warp per query row: merge the scores of one database chunk into the sorted (ascending) 32-entry candidate list
+__global__ void __launch_bounds__(256) tc_select_kernel(const float* __restrict__ S, long ldS, int rows, int ncols, int col0, float* __restrict__ cs,
+                                                        int* __restrict__ ci) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float Ls = cs[(long)r * TC_K + lane];
+    int Li = ci[(long)r * TC_K + lane];
+    float thr = __shfl_sync(0xffffffffu, Ls, 31);
+    const float* row = S + (long)r * ldS;
+    for (int base = 0; base < ncols; base += 32) {
+        const int j = base + lane;
+        const float sc = j < ncols ? row[j] : INFINITY;
+        unsigned mask = __ballot_sync(0xffffffffu, sc < thr);
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float vs = __shfl_sync(0xffffffffu, sc, b);
+            if (!(vs < thr)) continue;
+            const int vi = col0 + base + b;
+            const int pos = __popc(__ballot_sync(0xffffffffu, Ls <= vs));      // after equal scores: the earlier index stays first
+            const float us = __shfl_up_sync(0xffffffffu, Ls, 1);
+            const int ui = __shfl_up_sync(0xffffffffu, Li, 1);
+            if (lane > pos) { Ls = us; Li = ui; }
+            else if (lane == pos) { Ls = vs; Li = vi; }
+            thr = __shfl_sync(0xffffffffu, Ls, 31);
+        }
+    }
+    cs[(long)r * TC_K + lane] = Ls;
+    ci[(long)r * TC_K + lane] = Li;
+}
+
+// one warp per query: exact lane-order distance to the 32 candidates -> best; certificate against the 32nd score
+template <int CH>
+__global__ void __launch_bounds__(256) tc_rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, int nq, const float* __restrict__ qn,
+                                                        const float* __restrict__ cs, const int* __restrict__ ci, const float* __restrict__ vmax,
+                                                        unsigned long long* __restrict__ best, unsigned char* __restrict__ flags) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int lane = threadIdx.x & 31;
+    constexpr int d = CH * 128;
+    float4 qq[CH];
+    const float4* qr = reinterpret_cast<const float4*>(q + (long)qi * d);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) qq[c] = qr[c * 32 + lane];
+    const float Ls = cs[(long)qi * TC_K + lane];
+    const int Li = ci[(long)qi * TC_K + lane];
+    float bestd = INFINITY;
+    unsigned int besti = 0xffffffffu;
+    for (int c = 0; c < TC_K; ++c) {
+        const int id = __shfl_sync(0xffffffffu, Li, c);
+        if (id < 0) continue;
+        float4 v[CH];
+        const float4* vr = reinterpret_cast<const float4*>(db + (long long)id * d);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = __ldg(vr + k * 32 + lane);
+        const float dist = lane_order_dist<CH>(qq, v);
+        if (dist < bestd || (dist == bestd && (unsigned int)id < besti)) { bestd = dist; besti = (unsigned int)id; }
+    }
+    if (lane == 0) {
+        const float s32 = __shfl_sync(1u, Ls, 0) * 0.f + cs[(long)qi * TC_K + TC_K - 1];     // the worst kept score (inf: fewer than 32 rows)
+        const float eps = 3.f * 0.0009765625f * qn[2 * qi + 1] * vmax[0];
+        // a row outside the list has true score >= s32 - eps; it cannot beat (or tie) the winner if s32 + ||q||^2 - eps > d*
+        const bool sure = (besti != 0xffffffffu) && (s32 + qn[2 * qi] - eps > bestd * 1.0000005f + 1e-30f);
+        flags[qi] = sure ? 0 : 1;
+        best[qi] = sure ? (((unsigned long long)__float_as_uint(bestd) << 32) | besti) : ~0ull;
+    }
+}
+
+static void flat_tc_prepare(FlatTC& f, const float* db32, long long n, int d) {
+    RVCB_CHECK(d % 128 == 0 && d <= 1024 && n > 0 && n < 0x7fffffffLL, "knn: bad database shape");
+    f.db32 = db32; f.n = n; f.d = d;
+    CUDA_CHECK(cudaMalloc(&f.db16, sizeof(__half) * (size_t)n * d));
+    CUDA_CHECK(cudaMalloc(&f.vnorm, sizeof(float) * ((size_t)n + 4)));
+    CUDA_CHECK(cudaMemset(f.vnorm + n, 0, sizeof(float) * 4));
+    tc_prep_db_kernel<<<(unsigned)((n + 7) / 8), 256>>>(db32, n, d, f.db16, f.vnorm);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+static void flat_tc_workspace(FlatTC& f, int nq) {
+    if (nq <= f.q_cap) return;
+    const int want = std::max(nq, f.q_cap + f.q_cap / 2);
+    auto grab = [&](size_t bytes) { void* p = nullptr; CUDA_CHECK(cudaMalloc(&p, bytes)); f.owned.push_back(p); return p; };
+    f.q16 = (__half*)grab(sizeof(__half) * (size_t)want * f.d);
+    f.qn = (float*)grab(sizeof(float) * 2 * (size_t)want);
+    f.cs = (float*)grab(sizeof(float) * TC_K * (size_t)want);
+    f.ci = (int*)grab(sizeof(int) * TC_K * (size_t)want);
+    f.flags = (unsigned char*)grab((size_t)want);
+    if (!f.S) f.S = (float*)grab(sizeof(float) * (size_t)TC_QB * TC_NC);
+    f.q_cap = want;
+}
+
+// best[q] = pack(exact squared distance, row) of the nearest database row; bit-identical to top1()
+static void top1_tensor(FlatTC& f, const float* q, int nq, unsigned long long* best, cudaStream_t st) {
+    flat_tc_workspace(f, nq);
+    const int d = f.d;
+    tc_prep_q_kernel<<<ceil_div(nq, 8), 256, 0, st>>>(q, nq, d, f.q16, f.qn, f.cs, f.ci);
+    count_launch();
+    for (int q0 = 0; q0 < nq; q0 += TC_QB) {
+        const int qb = std::min(TC_QB, nq - q0);
+        for (long long r0 = 0; r0 < f.n; r0 += TC_NC) {
+            const int nc = (int)std::min<long long>(TC_NC, f.n - r0);
+            GemmArgs g;
+            g.A = f.q16 + (size_t)q0 * d; g.lda = d; g.a_rows = qb; g.a_cols = d;
+            g.B = f.db16 + (size_t)r0 * d; g.ldb = d; g.b_rows = nc; g.b_cols = d;
+            g.M = qb; g.N = nc; g.block_k = 64;
+            seg_linear(g, d);
+            g.bias = f.vnorm + r0;
+            g.out32 = f.S; g.ld32 = TC_NC;
+            gemm(g, st);
+            tc_select_kernel<<<ceil_div(qb, 8), 256, 0, st>>>(f.S, TC_NC, qb, nc, (int)r0, f.cs + (size_t)q0 * TC_K, f.ci + (size_t)q0 * TC_K);
+            count_launch();
+        }
+    }
+#define RVCB_RERANK(CH) case CH: tc_rerank_kernel<CH><<<ceil_div(nq, 8), 256, 0, st>>>(f.db32, q, nq, f.qn, f.cs, f.ci, f.vnorm + f.n, best, f.flags); break;
+    switch (d / 128) {
+        RVCB_RERANK(1) RVCB_RERANK(2) RVCB_RERANK(3) RVCB_RERANK(4) RVCB_RERANK(6) RVCB_RERANK(8)
+        default: RVCB_CHECK(false, "knn: unsupported dimension (128, 256, 384, 512, 768, 1024)");
+    }
+#undef RVCB_RERANK
+    KERNEL_CHECK();
+    count_launch();
+    top1(f.db32, f.n, d, q, nq, best, st, f.flags);          // exact search of the (rare) queries the certificate could not clear
+}
+
+void rvcb_index::destroy_coarse() { delete coarse_tc; coarse_tc = nullptr; }
+
+struct rvcb_flat {
+    FlatTC tc;
+    unsigned long long* best = nullptr;
+    int best_cap = 0;
+};
+
+static bool knn_tc_enabled(int nq) {
+    static int on = -1, min_q = 32;
+    if (on < 0) {
+        const char* e = getenv("RVCB_KNN_TC");
+        on = (e && e[0] == '0') ? 0 : 1;
+        const char* m = getenv("RVCB_KNN_TC_MINQ");
+        if (m) min_q = atoi(m);
+    }
+    return on && nq >= min_q;
 }
 
 // The coarse-assignment workspace grows geometrically and the outgrown block is kept until the index dies: a CUDA graph
@@ -255,6 +481,10 @@ int rvcb_index_create(const float* centroids, int nlist, const float* vectors, i
         ix->vectors = dev_upload(vectors, (size_t)ntotal * d);
         ix->list_off = dev_upload((const long long*)list_off, (size_t)nlist + 1);
         ix->list_ids = dev_upload((const long long*)list_ids, (size_t)ntotal);
+        if (nlist >= TC_K) {
+            ix->coarse_tc = new FlatTC();
+            flat_tc_prepare(*ix->coarse_tc, ix->centroids, nlist, d);
+        }
     } catch (...) {
         delete ix;
         throw;
@@ -270,7 +500,9 @@ int rvcb_index_search(rvcb_index* ix, const float* d_q, int nq, int k, float* d_
     RVCB_CHECK(ix && d_q && d_D && d_I && nq > 0, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     ensure_ws(ix, nq);
-    top1(ix->centroids, ix->nlist, ix->d, d_q, nq, ix->best, st);      // coarse quantiser, nprobe = 1
+    // coarse quantiser, nprobe = 1: query batches rank the centroids on the tensor cores and re-rank exactly (same result)
+    if (ix->coarse_tc && knn_tc_enabled(nq)) top1_tensor(*ix->coarse_tc, d_q, nq, ix->best, st);
+    else top1(ix->centroids, ix->nlist, ix->d, d_q, nq, ix->best, st);
     const int grid = ceil_div(nq, 8);
 #define RVCB_SCAN(K, CH) ivf_scan_kernel<K, CH><<<grid, 256, 0, st>>>(ix->vectors, ix->list_off, ix->list_ids, ix->best, d_q, nq, d_D, (long long*)d_I)
 #define RVCB_SCAN_K(CH)                                                       \
@@ -322,5 +554,41 @@ int rvcb_knn_bruteforce_top1(const float* d_db, int64_t n, int d, const float* d
 }
 
 void rvcb_index_destroy(rvcb_index* ix) { delete ix; }
+
+int rvcb_flat_create(const float* d_db, int64_t n, int d, rvcb_flat** out) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_db && out, "null argument");
+    auto* f = new rvcb_flat();
+    try {
+        flat_tc_prepare(f->tc, d_db, n, d);
+    } catch (...) {
+        delete f;
+        throw;
+    }
+    *out = f;
+    RVCB_API_END
+}
+
+int rvcb_flat_search_top1(rvcb_flat* f, const float* d_q, int nq, float* d_D, int64_t* d_I, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(f && d_q && nq > 0, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nq > f->best_cap) {
+        const int want = std::max(nq, f->best_cap + f->best_cap / 2);
+        unsigned long long* nb = nullptr;
+        CUDA_CHECK(cudaMalloc(&nb, sizeof(unsigned long long) * want));
+        f->tc.owned.push_back(nb);
+        f->best = nb;
+        f->best_cap = want;
+    }
+    if (knn_tc_enabled(nq) && f->tc.n >= TC_K) top1_tensor(f->tc, d_q, nq, f->best, st);
+    else top1(f->tc.db32, f->tc.n, f->tc.d, d_q, nq, f->best, st);
+    unpack_best_kernel<<<ceil_div(nq, 256), 256, 0, st>>>(f->best, nq, d_D, (long long*)d_I, nullptr);
+    KERNEL_CHECK();
+    count_launch();
+    RVCB_API_END
+}
+
+void rvcb_flat_destroy(rvcb_flat* f) { delete f; }
 
 }  // extern "C"

@@ -99,12 +99,20 @@ class RVC:
         ent["graph"].replay()
         return ent["out"].clone()
 
-    def _infer_body(self, wav_dev: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method, protect: float):
+    def _infer_body(self, wav_dev, block_frame_16k, skip_head, return_length, f0method, protect):
+        try:
+            return self._infer_body_impl(wav_dev, block_frame_16k, skip_head, return_length, f0method, protect)
+        except Exception:
+            engine.set_grid_cap(0)          # never leave the process-wide launch cap behind
+            raise
+
+    def _infer_body_impl(self, wav_dev: torch.Tensor, block_frame_16k: int, skip_head: int, return_length: int, f0method, protect: float):
         input_wav = wav_dev
         capturing = torch.cuda.is_current_stream_capturing()
         # content features + retrieval do not depend on f0: run them on a side stream while RMVPE runs on the main one
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
+        cap_prev = engine.set_grid_cap(engine.front_branch_cap())     # HuBERT / RMVPE side by side on disjoint SMs (restored before net_g)
         with torch.cuda.stream(self._side):
             logits = self.hubert.extract_features(source=wav_dev.view(1, -1), padding_mask=None, output_layer=9 if self.version == "v1" else 12)
             feats = self.hubert.final_proj(logits[0]) if self.version == "v1" else logits[0]
@@ -150,6 +158,7 @@ class RVC:
             self.cache_pitchf[4 - pitch.shape[0]:] = pitchf[3:-1]
             cache_pitch = self.cache_pitch[None, -p_len:]
             cache_pitchf = self.cache_pitchf[None, -p_len:] * return_length2 / return_length
+        engine.set_grid_cap(cap_prev)
         cur.wait_event(feats_ready)
         if not capturing:
             feats.record_stream(cur)

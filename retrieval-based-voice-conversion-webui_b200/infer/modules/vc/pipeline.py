@@ -195,14 +195,20 @@ class Pipeline(object):
             cur = torch.cuda.current_stream()
             fork = torch.cuda.Event()
             fork.record(cur)                       # the side stream depends on the padded audio only, not on RMVPE
-            # f0 first: RMVPE has the fewer launches, so both branches are in flight sooner when launching eagerly
-            pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
-            pitch, pitchf = pitch.unsqueeze(0), pitchf.unsqueeze(0)
-            self._side.wait_event(fork)
-            with torch.cuda.stream(self._side):
-                f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)
-                ev = torch.cuda.Event()
-                ev.record(self._side)
+            # the two branches are independent: cap their persistent grids at half the SMs each, so that kernels of the two
+            # streams run side by side instead of taking turns at the whole chip (measured: profiles/README.md, r2)
+            cap_prev = engine.set_grid_cap(engine.front_branch_cap())
+            try:
+                # f0 first: RMVPE has the fewer launches, so both branches are in flight sooner when launching eagerly
+                pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
+                pitch, pitchf = pitch.unsqueeze(0), pitchf.unsqueeze(0)
+                self._side.wait_event(fork)
+                with torch.cuda.stream(self._side):
+                    f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+            finally:
+                engine.set_grid_cap(cap_prev)
             if not capturing:
                 audio_pad.record_stream(self._side)
             self._prefetched = (audio_pad, f, f_raw, ev)

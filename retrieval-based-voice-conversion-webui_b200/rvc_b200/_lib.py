@@ -55,6 +55,7 @@ SIGNATURES = {
     "rvcb_last_error": (C.c_char_p, []),
     "rvcb_launch_count": (C.c_ulonglong, []),
     "rvcb_version": (C.c_char_p, []),
+    "rvcb_set_grid_cap": (_I, [_I]),
     "rvcb_prof_begin": (_I, []),
     "rvcb_prof_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "rvcb_prof_classes": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -75,6 +76,9 @@ SIGNATURES = {
     "rvcb_index_blend": (_I, [_P, _P, _I, _I, _P, _P, _F, _P, _P]),
     "rvcb_knn_bruteforce_top1": (_I, [_P, _L, _I, _P, _I, _P, _P, _P]),
     "rvcb_index_destroy": (None, [_P]),
+    "rvcb_flat_create": (_I, [_P, _L, _I, C.POINTER(_P)]),
+    "rvcb_flat_search_top1": (_I, [_P, _P, _I, _P, _P, _P]),
+    "rvcb_flat_destroy": (None, [_P]),
     "rvcb_upsample_protect": (_I, [_P, _P, _I, _I, _P, _I, _F, _P, _P]),
     "rvcb_post_mix": (_I, [_P, _L, _I, _P, _L, _F, _P, _P]),
     "rvcb_host_filtfilt": (_I, [_P, _P, _P, _I, _P, _I, _L, _P]),

@@ -19,6 +19,17 @@ def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+def set_grid_cap(max_ctas: int) -> int:
+    """Cap the persistent GEMM / kNN grids launched from now on (0 = all SMs); returns the previous cap."""
+    return _lib.lib().rvcb_set_grid_cap(int(max_ctas))
+
+
+def front_branch_cap() -> int:
+    """CTAs per kernel while the two front branches are launched (RVCB_FRONT_CAP, default: half of the 148 SMs)."""
+    import os
+    return int(os.environ.get("RVCB_FRONT_CAP", "74"))
+
+
 def _chk_dev(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
@@ -155,6 +166,31 @@ def knn_bruteforce_top1(db: torch.Tensor, q: torch.Tensor) -> Tuple[torch.Tensor
     I = torch.empty(q.shape[0], device=q.device, dtype=torch.int64)
     _lib.check(_lib.lib().rvcb_knn_bruteforce_top1(_p(db), db.shape[0], db.shape[1], _p(q), q.shape[0], _p(D), _p(I), _stream_ptr()))
     return D, I
+
+
+class FlatIndex:
+    """Exact brute-force L2 top-1 over a device-resident fp32 database, tensor-core short list for query batches
+    (rvcb_flat_*): results bit-identical to ``knn_bruteforce_top1``."""
+
+    def __init__(self, db: torch.Tensor):
+        _lib.init(db.device.index or 0)
+        self.db = _chk_dev(db, torch.float32, "db")          # kept alive: the handle reads it
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().rvcb_flat_create(_p(self.db), self.db.shape[0], self.db.shape[1], C.byref(self.h)))
+
+    def search(self, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = _chk_dev(q.reshape(-1, self.db.shape[1]), torch.float32, "q")
+        D = torch.empty(q.shape[0], device=q.device, dtype=torch.float32)
+        I = torch.empty(q.shape[0], device=q.device, dtype=torch.int64)
+        _lib.check(_lib.lib().rvcb_flat_search_top1(self.h, _p(q), q.shape[0], _p(D), _p(I), _stream_ptr()))
+        return D, I
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_flat_destroy(self.h)
+        except Exception:
+            pass
 
 
 def upsample_protect(feats: torch.Tensor, feats0: Optional[torch.Tensor], pitchf: Optional[torch.Tensor], T: int, protect: float) -> torch.Tensor:

@@ -65,3 +65,27 @@ def test_bruteforce_large_property():
     rows = torch.tensor([0, 17, 999_999, 123_456, 500_000], device="cuda")
     D, I = knn_bruteforce_top1(db, db[rows].clone())
     assert torch.equal(I, rows) and (D == 0).all()
+
+
+@pytest.mark.parametrize("N,nq", [(5000, 40), (70000, 700), (33000, 2100)])
+def test_flat_tensor_core_short_list_is_bit_identical_to_the_exact_scan(N, nq):
+    """rvcb_flat_search_top1 (fp16 GEMM scores -> 32 candidates -> exact lane-order re-rank + rounding certificate) vs the
+    exact SIMT scan: D and I bit for bit, including exact duplicates in the database (ties -> lowest row) and near-ties."""
+    import torch
+    from rvc_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(N + nq)
+    db = torch.randn(N, 768, device="cuda", generator=g) * 0.3
+    db[N // 2: N // 2 + 50] = db[7]                                   # 51 identical rows
+    db[100:140] = db[99] + 1e-4 * torch.randn(40, 768, device="cuda", generator=g)      # near-duplicates inside fp16 resolution
+    q = db[torch.randint(0, N, (nq,), device="cuda", generator=g)] + 0.03 * torch.randn(nq, 768, device="cuda", generator=g)
+    q[0] = db[7]
+    q[1] = db[99]
+    q[2] = db[120] + 1e-5
+    D0, I0 = engine.knn_bruteforce_top1(db, q)
+    flat = engine.FlatIndex(db)
+    D1, I1 = flat.search(q)
+    assert torch.equal(I0, I1) and torch.equal(D0, D1)
+    assert int(I1[0]) == 7                                            # lowest of the 51 identical rows
+    # small batches take the scan itself
+    D2, I2 = flat.search(q[:5])
+    assert torch.equal(I2, I0[:5]) and torch.equal(D2, D0[:5])

@@ -14,10 +14,10 @@ from rvc_b200.index_build import build_ivf_layout  # noqa: E402
 
 _lib.init(0)
 try:
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    src = "measured"
+    _pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    peak, tpeak, src = _pk["hbm_gbs"], _pk["bf16_tflops"], "measured"
 except Exception:
-    peak, src = 6650.0, "fallback"
+    peak, tpeak, src = 6650.0, 1590.0, "fallback"
 
 
 def timeit(fn, reps=10, warm=3):
@@ -37,6 +37,7 @@ print(f"# brute-force L2 top-1, d=768 fp32; HBM peak {peak} GB/s ({src}); bytes 
 g = torch.Generator(device="cuda").manual_seed(0)
 for N in (10_000, 100_000, 1_000_000, 10_000_000):
     db = torch.randn(N, 768, device="cuda", generator=g)
+    flat = engine.FlatIndex(db)
     for nq in (1, 8, 32, 64, 512, 4096):
         if N * nq > 1.1e10:
             continue
@@ -45,9 +46,16 @@ for N in (10_000, 100_000, 1_000_000, 10_000_000):
         tiles = (nq + 31) // 32
         gbs = N * 768 * 4 * tiles / (ms * 1e-3) / 1e9
         D, I = engine.knn_bruteforce_top1(db, q)
-        print(f"N={N:>9} nq={nq:>5}  {ms:9.3f} ms  {gbs:8.1f} GB/s (db bytes x query tiles)  frac_of_hbm_peak={gbs / peak:5.2f}  "
-              f"single-pass GB/s={N * 768 * 4 / (ms * 1e-3) / 1e9:8.1f}")
-    del db
+        line = (f"N={N:>9} nq={nq:>5}  exact scan {ms:9.3f} ms  {gbs:8.1f} GB/s (db bytes x query tiles)  frac_of_hbm_peak={gbs / peak:5.2f}  "
+                f"single-pass GB/s={N * 768 * 4 / (ms * 1e-3) / 1e9:8.1f}")
+        if nq >= 32:
+            # tensor-core short list + exact re-rank (rvcb_flat_*): same D / I; tensor roofline = 2*nq*N*768 flops
+            ms2 = timeit(lambda: flat.search(q), reps=5 if N >= 1_000_000 else 20)
+            D2, I2 = flat.search(q)
+            tf = 2.0 * nq * N * 768 / (ms2 * 1e-3) / 1e12
+            line += f"  | tensor short-list {ms2:9.3f} ms  {tf:7.1f} TFLOP/s  frac_of_bf16_peak={tf / tpeak:5.3f}  identical={bool(torch.equal(I, I2) and torch.equal(D, D2))}"
+        print(line)
+    del flat, db
 lay = build_ivf_layout(SY.index_vectors(100000, 768, 0).numpy(), None, seed=0, device="cuda")
 ix = engine.Index.from_oracle_layout(lay)
 for nq in (1, 135, 799, 4096):
