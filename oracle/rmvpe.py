@@ -79,7 +79,7 @@ def _gru_module(w: W) -> torch.nn.GRU:
     if key not in _GRU_CACHE:
         gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True)
         gru.load_state_dict({k[len("fc.0.gru."):]: v for k, v in w.items() if k.startswith("fc.0.gru.")})
-        _GRU_CACHE[key] = gru.to(device=ref.device, dtype=ref.dtype).eval()
+        _GRU_CACHE[key] = gru.to(device=ref.device, dtype=ref.dtype).eval().requires_grad_(False)
     return _GRU_CACHE[key]
 
 

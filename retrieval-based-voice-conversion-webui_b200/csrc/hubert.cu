@@ -7,6 +7,7 @@
 // [T/2, 2C] view so that stride disappears into the K dimension (no im2col).
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
+#include "attn_fused.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "weights.cuh"
@@ -232,24 +233,33 @@ static void hubert_forward(rvcb_hubert* h, const float* d_wav, int n, int output
             g.bias = L.bv; g.bias_per_row = 1; g.out16 = vT16; g.ld16 = Tp;
             gemm(g, st);
         }
-        {   // S[h] = q_h k_h^T
-            GemmArgs g;
-            g.A = qk16; g.lda = 1536; g.a_rows = T; g.a_cols = 768;
-            g.B = qk16; g.ldb = 1536; g.b_rows = T; g.b_cols = 1536;
-            g.M = T; g.N = T; seg_linear(g, 64);
-            g.batch = 12; g.a_col_z = 64; g.b_col0 = 768; g.b_col_z = 64; g.c_z = (long)T * Tp;
-            g.out32 = S32; g.ld32 = Tp;
-            gemm(g, st);
-        }
-        softmax_rows(S32, Tp, 12, T, P16, Tp, nullptr, 0, 0, nullptr, st);
-        {   // ctx[:, h] = P_h V_h
-            GemmArgs g;
-            g.A = P16; g.lda = Tp; g.a_rows = 12 * T; g.a_cols = T;
-            g.B = vT16; g.ldb = Tp; g.b_rows = 768; g.b_cols = T;
-            g.M = T; g.N = 64; seg_linear(g, T);
-            g.batch = 12; g.a_row_z = T; g.b_row_z = 64; g.c_z = 64;
-            g.out16 = ctx16; g.ld16 = 768;
-            gemm(g, st);
+        static const bool fused_attn = [] { const char* e = getenv("RVCB_ATTN"); return e && e[0] == '1'; }();      // opt-in until validated on the GPU
+        AttnFusedArgs at;
+        at.q = qk16; at.ldq = 1536; at.k = qk16 + 768; at.ldk = 1536; at.vT = vT16; at.ldv = Tp; at.T = T; at.heads = 12; at.dh = 64;
+        at.out = ctx16; at.ldo = 768;
+        if (fused_attn && attention_fused_supported(at)) {
+            // one launch: scores stay in TMEM, probabilities in shared memory (attn_fused.cu)
+            attention_fused(at, st);
+        } else {
+            {   // S[h] = q_h k_h^T
+                GemmArgs g;
+                g.A = qk16; g.lda = 1536; g.a_rows = T; g.a_cols = 768;
+                g.B = qk16; g.ldb = 1536; g.b_rows = T; g.b_cols = 1536;
+                g.M = T; g.N = T; seg_linear(g, 64);
+                g.batch = 12; g.a_col_z = 64; g.b_col0 = 768; g.b_col_z = 64; g.c_z = (long)T * Tp;
+                g.out32 = S32; g.ld32 = Tp;
+                gemm(g, st);
+            }
+            softmax_rows(S32, Tp, 12, T, P16, Tp, nullptr, 0, 0, nullptr, st);
+            {   // ctx[:, h] = P_h V_h
+                GemmArgs g;
+                g.A = P16; g.lda = Tp; g.a_rows = 12 * T; g.a_cols = T;
+                g.B = vT16; g.ldb = Tp; g.b_rows = 768; g.b_cols = T;
+                g.M = T; g.N = 64; seg_linear(g, T);
+                g.batch = 12; g.a_row_z = T; g.b_row_z = 64; g.c_z = 64;
+                g.out16 = ctx16; g.ld16 = 768;
+                gemm(g, st);
+            }
         }
         {   // out proj + residual
             GemmArgs g;

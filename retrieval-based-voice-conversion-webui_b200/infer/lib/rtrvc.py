@@ -112,7 +112,9 @@ class RVC:
         # content features + retrieval do not depend on f0: run them on a side stream while RMVPE runs on the main one
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
-        cap_prev = engine.set_grid_cap(engine.front_branch_cap())     # HuBERT / RMVPE side by side on disjoint SMs (restored before net_g)
+        # the offline pipeline caps the two front branches at half the SMs each (side by side); on the short realtime window the
+        # cap measured slower (p50 3.64 vs 3.48 ms per block): RVCB_RT_FRONT_CAP opts in
+        cap_prev = engine.set_grid_cap(int(os.environ.get("RVCB_RT_FRONT_CAP", "0")))
         with torch.cuda.stream(self._side):
             logits = self.hubert.extract_features(source=wav_dev.view(1, -1), padding_mask=None, output_layer=9 if self.version == "v1" else 12)
             feats = self.hubert.final_proj(logits[0]) if self.version == "v1" else logits[0]

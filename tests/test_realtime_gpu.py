@@ -37,7 +37,7 @@ def test_rtrvc_blocks_match_oracle_given_the_pitch_ring():
         assert y.shape == ref.shape == (RET * 480,)
         err = np.abs(y - ref).max()
         print(f"[parity] realtime block {b} (shared pitch ring + noise): max abs err {err:.3e}")
-        assert err < 2e-3, (b, err)
+        assert err < 1e-3, (b, err)          # measured 3.6e-4 .. 5.1e-4
 
 
 def test_rtrvc_rmvpe_path_pitch_ring_and_graph_replay():
@@ -66,7 +66,7 @@ def test_rtrvc_rmvpe_path_pitch_ring_and_graph_replay():
         print(f"[parity] realtime block {b} (own RMVPE, {'graph' if any('graph' in e for e in rt._graphs.values()) else 'eager'}): "
               f"ring coarse same {same:.4f}, median |df0|/f0 {rel:.2e}, waveform rel RMS err {rms:.3e}")
         assert same >= 0.97 and rel < 1e-3
-        assert rms < 0.08          # f0 differences of ~1e-5 integrate into the NSF sine phase over the 2.7 s window
+        assert rms < 5e-3          # measured 7e-4 .. 8e-4: f0 differences of ~1e-5 integrate into the NSF sine phase over the 2.7 s window
     assert any("graph" in e for e in rt._graphs.values())
 
 
