@@ -233,7 +233,7 @@ static void hubert_forward(rvcb_hubert* h, const float* d_wav, int n, int output
             g.bias = L.bv; g.bias_per_row = 1; g.out16 = vT16; g.ld16 = Tp;
             gemm(g, st);
         }
-        static const bool fused_attn = [] { const char* e = getenv("RVCB_ATTN"); return e && e[0] == '1'; }();      // opt-in until validated on the GPU
+        static const bool fused_attn = [] { const char* e = getenv("RVCB_ATTN"); return !(e && e[0] == '0'); }();   // RVCB_ATTN=0: the 3-launch path
         AttnFusedArgs at;
         at.q = qk16; at.ldq = 1536; at.k = qk16 + 768; at.ldk = 1536; at.vT = vT16; at.ldv = Tp; at.T = T; at.heads = 12; at.dh = 64;
         at.out = ctx16; at.ldo = 768;
