@@ -235,7 +235,7 @@ static void hubert_forward(rvcb_hubert* h, const float* d_wav, int n, int output
         }
         static const bool fused_attn = [] { const char* e = getenv("RVCB_ATTN"); return !(e && e[0] == '0'); }();   // RVCB_ATTN=0: the 3-launch path
         AttnFusedArgs at;
-        at.q = qk16; at.ldq = 1536; at.k = qk16 + 768; at.ldk = 1536; at.vT = vT16; at.ldv = Tp; at.T = T; at.heads = 12; at.dh = 64;
+        at.q = qk16; at.ldq = 1536; at.k = qk16 + 768; at.ldk = 1536; at.vT = vT16; at.ldv = Tp; at.T = T; at.heads = 12; at.dk = 64; at.dv = 64;
         at.out = ctx16; at.ldo = 768;
         if (fused_attn && attention_fused_supported(at)) {
             // one launch: scores stay in TMEM, probabilities in shared memory (attn_fused.cu)

@@ -6,6 +6,7 @@
 // resblock accumulators stay fp32 (that is what holds the 1e-3 waveform bound).
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
+#include "attn_fused.cuh"
 #include "gemm.cuh"
 #include <algorithm>
 #include "kernels.cuh"
@@ -21,6 +22,7 @@ namespace {
 struct AttnLayer {
     PackedB wqk, wv, wo, ek, evT, w1, w2;
     float *bqk, *bv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    float* ev32 = nullptr;         // emb_rel_v as fp32 [21, kc] (fused attention)
 };
 struct FlowLayer {
     PackedB pre, in[3], res[2], skip[3], post;
@@ -136,6 +138,7 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
                 for (int r = 0; r < R; ++r)
                     for (int d = 0; d < kc; ++d) t[(size_t)d * 64 + r] = ev.data[(size_t)r * kc + d];
                 L.evT = upload_half(own, t, pad_to(kc, 128), 64);
+                L.ev32 = own.upload(ev.data);
             }
             L.ln1_g = own.upload(w.get("enc_p.encoder.norm_layers_1." + std::to_string(l) + ".gamma").data);
             L.ln1_b = own.upload(w.get("enc_p.encoder.norm_layers_1." + std::to_string(l) + ".beta").data);
@@ -372,15 +375,6 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             g.bias = L.bv; g.bias_per_row = 1; g.out16 = vT16; g.ld16 = Tp;
             gemm(g, st);
         }
-        {   // scores = (q k^T) / sqrt(kc)
-            GemmArgs g;
-            g.A = qk16; g.lda = NQK; g.a_rows = T; g.a_cols = heads * HP;
-            g.B = qk16; g.ldb = NQK; g.b_rows = T; g.b_cols = NQK;
-            g.M = T; g.N = T; seg_linear(g, HP);
-            g.batch = heads; g.a_col_z = HP; g.b_col0 = heads * HP; g.b_col_z = HP; g.c_z = (long)T * Tp;
-            g.alpha = qscale; g.out32 = S32; g.ld32 = Tp;
-            gemm(g, st);
-        }
         {   // relative-key logits (q / sqrt(kc)) E_k^T  -> [heads, T, 32]
             GemmArgs g = mk(qk16, NQK, T, heads * HP, L.ek, T, 32);
             seg_linear(g, HP);
@@ -388,22 +382,42 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
             g.alpha = qscale; g.out32 = qrel32; g.ld32 = 32;
             gemm(g, st);
         }
-        softmax_rows(S32, Tp, heads, T, P16, Tp, qrel32, 32, 10, prel16, st);
-        {   // P V
-            GemmArgs g;
-            g.A = P16; g.lda = Tp; g.a_rows = heads * T; g.a_cols = T;
-            g.B = vT16; g.ldb = Tp; g.b_rows = H; g.b_cols = T;
-            g.M = T; g.N = kc; seg_linear(g, T);
-            g.batch = heads; g.a_row_z = T; g.b_row_z = kc; g.c_z = kc;
-            g.out32 = ctx32; g.ld32 = H;
-            gemm(g, st);
-        }
-        {   // + relative values: sum_r P[i, i+r-10] E_v[r]
-            GemmArgs g = mk(prel16, 64, heads * T, 64, L.evT, T, kc);
-            seg_linear(g, 64);
-            g.batch = heads; g.a_row_z = T; g.c_z = kc;
-            g.res2 = ctx32; g.ldres2 = H; g.out16 = ctx16; g.ld16 = H;
-            gemm(g, st);
+        // Measured (profiles/README.md, r2g): 181 us per layer against ~85 us for the five small launches below -- 2 heads x 13 query
+        // blocks are only 26 CTAs, each walking 13 key blocks twice with one softmax warp per SM sub-partition.  Opt-in.
+        static const bool fused_attn = [] { const char* e = getenv("RVCB_ATTN_REL"); return e && e[0] == '1'; }();
+        AttnFusedArgs at;
+        at.q = qk16; at.ldq = NQK; at.k = qk16 + (size_t)heads * HP; at.ldk = NQK; at.vT = vT16; at.ldv = Tp; at.T = T; at.heads = heads;
+        at.dk = HP; at.dv = kc; at.qscale = qscale; at.qrel = qrel32; at.ev = L.ev32; at.out = ctx16; at.ldo = H;
+        if (fused_attn && attention_fused_supported(at)) {
+            // scores in TMEM, probabilities in shared memory, band logits / band values applied in place (attn_fused.cu)
+            attention_fused(at, st);
+        } else {
+            {   // scores = (q k^T) / sqrt(kc)
+                GemmArgs g;
+                g.A = qk16; g.lda = NQK; g.a_rows = T; g.a_cols = heads * HP;
+                g.B = qk16; g.ldb = NQK; g.b_rows = T; g.b_cols = NQK;
+                g.M = T; g.N = T; seg_linear(g, HP);
+                g.batch = heads; g.a_col_z = HP; g.b_col0 = heads * HP; g.b_col_z = HP; g.c_z = (long)T * Tp;
+                g.alpha = qscale; g.out32 = S32; g.ld32 = Tp;
+                gemm(g, st);
+            }
+            softmax_rows(S32, Tp, heads, T, P16, Tp, qrel32, 32, 10, prel16, st);
+            {   // P V
+                GemmArgs g;
+                g.A = P16; g.lda = Tp; g.a_rows = heads * T; g.a_cols = T;
+                g.B = vT16; g.ldb = Tp; g.b_rows = H; g.b_cols = T;
+                g.M = T; g.N = kc; seg_linear(g, T);
+                g.batch = heads; g.a_row_z = T; g.b_row_z = kc; g.c_z = kc;
+                g.out32 = ctx32; g.ld32 = H;
+                gemm(g, st);
+            }
+            {   // + relative values: sum_r P[i, i+r-10] E_v[r]
+                GemmArgs g = mk(prel16, 64, heads * T, 64, L.evT, T, kc);
+                seg_linear(g, 64);
+                g.batch = heads; g.a_row_z = T; g.c_z = kc;
+                g.res2 = ctx32; g.ldres2 = H; g.out16 = ctx16; g.ld16 = H;
+                gemm(g, st);
+            }
         }
         {
             GemmArgs g = mk(ctx16, H, T, H, L.wo, T, H);

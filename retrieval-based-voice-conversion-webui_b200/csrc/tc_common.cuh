@@ -223,12 +223,14 @@ inline void encode_map_ex(CUtensorMap* map, const void* base, CUtensorMapDataTyp
 // launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (enabled with RVCB_PDL=1)
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
-    static int use_pdl = -1;
+    static int use_pdl = -1, pdl_max_grid = 100;
     if (use_pdl < 0) {
         const char* e = getenv("RVCB_PDL");
-        // measured (profiles/README.md): -0.6 ms on the serial step, neutral-to-slightly-negative when RMVPE shares the GPU on a
-        // side stream (early CTAs park on SMs the other stream could use) -> opt-in
-        use_pdl = (e && e[0] == '1') ? 1 : 0;
+        // measured (profiles/README.md): 1 (every launch) is neutral-to-negative -- early CTAs of big grids park on SMs the other
+        // stream could use and 226 KB CTAs cannot co-reside anyway.  2: only launches of at most RVCB_PDL_MAXGRID CTAs, whose
+        // prologue (TMEM alloc, barrier init, tensor-map fetch) then overlaps the predecessor's tail on idle SMs.
+        use_pdl = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0);
+        if (const char* m = getenv("RVCB_PDL_MAXGRID")) pdl_max_grid = atoi(m);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -239,7 +241,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.numAttrs = (use_pdl == 1 || (use_pdl == 2 && grid <= pdl_max_grid)) ? 1 : 0;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
