@@ -72,12 +72,33 @@ class HubertB200:
 
     @torch.no_grad()
     def extract_features(self, source, padding_mask=None, mask=False, output_layer=None):
-        if source.dim() != 2 or source.shape[0] != 1:
-            raise ValueError("B=1 only (the reference callers never batch)")
+        """source [B, N]; padding_mask bool [B, N] (True = padding, trailing).  B = 1 without padding is the reference callers'
+        case (pipeline.py:100-110) and the hot path.  B > 1 is the batched front door: every utterance is run over
+        its own valid samples and the results are stacked, zero-padded to the longest -- frame for frame what B = 1 calls return
+        (the kernels themselves are B = 1: independent utterances overlap as separate streams / graphs, not as packed GEMMs).
+        Returns (features [B, T_max, 768], frame padding mask [B, T_max] or None)."""
+        if source.dim() != 2:
+            raise ValueError("source must be [B, N]")
+        layer = 12 if output_layer is None else int(output_layer)
+        B = source.shape[0]
+        lens = [source.shape[1]] * B
         if padding_mask is not None and bool(padding_mask.any()):
-            raise NotImplementedError("padding_mask with True entries (batched front door) is a 'next' row (SURVEY §8f-3)")
-        feats = self._m.extract(source[0].to(self.device), 12 if output_layer is None else int(output_layer))
-        return feats.unsqueeze(0), None
+            pm = padding_mask.to("cpu")
+            for b in range(B):
+                n_valid = int((~pm[b]).sum())
+                if bool(pm[b, :n_valid].any()):
+                    raise ValueError("padding_mask must mark trailing padding only")
+                lens[b] = n_valid
+        if B == 1 and lens[0] == source.shape[1]:
+            return self._m.extract(source[0].to(self.device), layer).unsqueeze(0), None
+        outs = [self._m.extract(source[b, : lens[b]].to(self.device), layer) for b in range(B)]
+        T = max(o.shape[0] for o in outs)
+        feats = torch.zeros(B, T, outs[0].shape[1], device=self.device)
+        fmask = torch.ones(B, T, dtype=torch.bool, device=self.device)
+        for b, o in enumerate(outs):
+            feats[b, : o.shape[0]] = o
+            fmask[b, : o.shape[0]] = False
+        return feats, (fmask if bool(fmask.any()) else None)
 
     @torch.no_grad()
     def final_proj(self, x):

@@ -52,8 +52,23 @@ class SynthesizerB200:
     def infer(self, phone: torch.Tensor, phone_lengths: torch.Tensor, sid: torch.Tensor, pitch: Optional[torch.Tensor] = None,
               pitchf: Optional[torch.Tensor] = None, skip_head: Optional[int] = None, return_length: Optional[int] = None,
               return_length2: Optional[int] = None) -> torch.Tensor:
-        if phone.dim() != 3 or phone.shape[0] != 1:
-            raise ValueError("B200 synthesizer is strictly B=1 like the reference callers (pipeline.py:164, rtrvc.py:236)")
+        if phone.dim() != 3:
+            raise ValueError("phone must be [B, T, C]")
+        if phone.shape[0] != 1:
+            # batched front door: sequence_mask semantics (rvc/layers/utils.py:58-65) by running every utterance over
+            # its own phone_lengths[b] frames; outputs are stacked and zero-padded to the longest.  The reference callers are B = 1.
+            if skip_head is not None or return_length is not None or return_length2 is not None:
+                raise ValueError("the realtime arguments are B = 1 only")
+            outs = []
+            for b in range(phone.shape[0]):
+                Tb = int(phone_lengths.reshape(-1)[b])
+                outs.append(self.infer(phone[b: b + 1, :Tb], torch.tensor([Tb]), sid.reshape(-1)[b: b + 1] if sid.numel() > 1 else sid,
+                                       None if pitch is None else pitch[b: b + 1, :Tb], None if pitchf is None else pitchf[b: b + 1, :Tb])[0, 0])
+            n = max(o.shape[0] for o in outs)
+            y = torch.zeros(len(outs), 1, n, device=self.device)
+            for b, o in enumerate(outs):
+                y[b, 0, : o.shape[0]] = o
+            return y
         T = phone.shape[1]
         if int(phone_lengths.reshape(-1)[0]) != T:
             raise ValueError("phone_lengths must equal the number of phone frames")

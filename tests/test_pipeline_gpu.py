@@ -279,3 +279,39 @@ def test_device_resident_utterance_path_equals_host_path():
     for r in reps:
         assert r.shape == b.shape and np.abs(r).max() > 1000
         assert abs(np.sqrt(np.mean(r ** 2)) / np.sqrt(np.mean(b ** 2)) - 1) < 0.05
+
+
+def test_batched_front_door_equals_per_utterance_calls():
+    """padding_mask through the HuBERT object and phone_lengths (sequence_mask) through the synthesizer container for B in {2, 3}:
+    frame for frame / sample for sample what the B = 1 calls return (the kernels stay B = 1)."""
+    from infer.modules.vc.utils import HubertB200
+    from rvc.synthesizer import get_synthesizer
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.0, 600)
+    hub = HubertB200(hw, "cuda:0")
+    lens = [16000, 11000, 13500]
+    wavs = [OW.synth_voice(1.0, seed=40 + i)[:n] for i, n in enumerate(lens)]
+    src = torch.zeros(3, 16000)
+    pm = torch.ones(3, 16000, dtype=torch.bool)
+    for b, w in enumerate(wavs):
+        src[b, : len(w)] = w
+        pm[b, : len(w)] = False
+    feats, fmask = hub.extract_features(source=src.cuda(), padding_mask=pm.cuda(), output_layer=12)
+    for b, w in enumerate(wavs):
+        one = hub.extract_features(source=w[None].cuda(), padding_mask=None, output_layer=12)[0][0]
+        assert torch.equal(feats[b, : one.shape[0]], one) and bool((feats[b, one.shape[0]:] == 0).all())
+        assert fmask is not None and int((~fmask[b]).sum()) == one.shape[0]
+    net_g, _ = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
+    Ts = [40, 28]
+    g = torch.Generator().manual_seed(1)
+    phone = torch.randn(2, 40, 768, generator=g).cuda() * 0.5
+    pitch = torch.randint(1, 200, (2, 40), generator=g).cuda()
+    pitchf = (torch.rand(2, 40, generator=g) * 300 + 80).cuda()
+    noises = [(torch.randn(1, 192, T, generator=g), torch.randn(1, T * 480, 1, generator=g)) for T in Ts]
+    for n in noises:
+        net_g.set_noise(*n)
+    yb = net_g.infer(phone, torch.tensor(Ts), torch.tensor([0, 0]), pitch, pitchf)
+    assert yb.shape == (2, 1, 40 * 480)
+    for b, T in enumerate(Ts):
+        net_g.set_noise(*noises[b])
+        y1 = net_g.infer(phone[b: b + 1, :T], torch.tensor([T]), torch.tensor([0]), pitch[b: b + 1, :T], pitchf[b: b + 1, :T])[0, 0]
+        assert torch.equal(yb[b, 0, : T * 480], y1) and bool((yb[b, 0, T * 480:] == 0).all())
