@@ -10,6 +10,7 @@
 // are SIMT.
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
+#include "conv2d_row.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "weights.cuh"
@@ -529,6 +530,10 @@ __global__ void decode_kernel(const float* __restrict__ sal, int T, float thred,
 // ------------------------------------------------------------------------------------------------
 static void conv3x3(const ConvBN& c, const __half* x, long ldx, int Hh, int W, int act, const float* res2, long ldres2, float* out32,
                     long ld32, __half* out16, long ld16, cudaStream_t st) {
+    if (act == ACT_RELU || act == ACT_NONE) {      // full-resolution 16-channel levels: one halo load per image row (conv2d_row.cu)
+        const Conv2dRowArgs a{x, ldx, Hh, W, c.cin, c.cout, c.w.d, c.w.rows, c.w.cols, c.b, act == ACT_RELU, res2, ldres2, out32, ld32, out16, ld16};
+        if (conv2d_row_try(a, st)) return;
+    }
     GemmArgs g;
     g.A = x; g.lda = ldx; g.a_rows = Hh; g.a_cols = c.cin; g.conv2d_W = W;
     g.B = c.w.d; g.ldb = c.w.cols; g.b_rows = c.w.rows; g.b_cols = c.w.cols;
