@@ -312,6 +312,33 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- the same step with the synthesizer decoding EVERY frame (RVCB_TRIM=0), i.e. without restricting the flow / decoder to the
+    # frames the caller keeps (the x_pad context is discarded at pipeline.py:295); the kept samples are bit-identical either way ----
+    full_decode = None
+    if use_graph:
+        try:
+            os.environ["RVCB_TRIM"] = "0"
+            for _ in range(2):
+                dev_step()
+            torch.cuda.synchronize()
+            g_full = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_full):
+                out_full = dev_step()
+            fms = timed(g_full.replay, args.steps, args.warmup)
+            graph.replay()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(out_full, graph_out)) if (out_full.dtype == graph_out.dtype and out_full.shape == graph_out.shape) else None
+            full_decode = {"ms_per_step": fms / args.steps, "value": world * args.steps * OUT_SAMPLES / (fms * 1e-3), "unit": "samples/s",
+                           "what": "RVCB_TRIM=0: flow + decoder over all 1598 frames incl. the 2 x 3 s of x_pad context that pipeline.py:295 discards",
+                           "int16_output_identical_to_trimmed_step": same,
+                           "note": "noise is drawn inside each graph, so the two int16 outputs are only compared when the draws coincide; "
+                                   "tests/test_synth_gpu.py proves bit-equality of the kept samples on shared noise"}
+        except Exception as e:
+            full_decode = {"error": str(e)}
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("RVCB_TRIM", None)
+
     # ---- throughput mode: several utterances in flight on one GPU (batch conversion, BASELINE config #4's per-GPU work): every
     # utterance is its own captured graph over its own handles (arenas are per handle) replayed on its own stream; a single
     # utterance is latency-bound (two branches of ~200 small launches), so independent utterances fill the idle SMs ----
@@ -397,7 +424,8 @@ def main():
     ws_ms, ws_n, ws_flops, ws_bytes = cls[0][1] / 3, cls[1][1] / 3, cls[2][1] / 3, cls[3][1] / 3
     fu_ms, fu_n, fu_flops, fu_bytes = cls[0][2] / 3, cls[1][2] / 3, cls[2][2] / 3, cls[3][2] / 3
     pk, pk_src = peaks()
-    achieved = ALGO_FLOPS / (gemm_ms_per_step * 1e-3) / 1e12
+    exec_flops = (cls[2][0] + cls[2][1] + cls[2][2]) / 3          # executed 2*M*N*K of every tcgen05 launch (incl. K padding), per step
+    achieved = exec_flops / (gemm_ms_per_step * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     voc_ms, voc_flops = fu_ms + ws_ms, fu_flops + ws_flops
 
@@ -409,6 +437,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate+residuals",
         "data": "synthetic", "rtf_x_per_gpu": value / world / 48000.0,
         "config": {"workload": WORKLOAD},
+        "decoder_trim": "flow / decoder run over the kept frames + receptive-field margins (1030 + 80 of 1598 frames); kept samples bit-identical "
+                        "to the full decode (rvcb_synth_infer_keep, tests/test_synth_gpu.py); 'full_decode' times the untrimmed step",
         "timing": {"l2": "256 MiB flush between timed iterations", "utterances_per_gpu_per_step": 1,
                    "device_step": f"CUDA graph replay of the {int(launches)}-launch step" if use_graph else "eager launches"},
         "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": int(160000 * 4 + 8),   # the utterance (float32, one pinned copy) + speaker id
@@ -420,6 +450,7 @@ def main():
         "clocks": sampler.summary(),
         "realtime": realtime,
         "throughput_concurrent": conc_res,
+        "full_decode": full_decode,
         # dominant kernel by work: the vocoder's residual-block convolutions (stages 2-3: one fused launch per residual block,
         # resblock_fused_kernel; 27 % of the utterance's FLOPs).  Tensor-bound by design: x in / y out are the only HBM traffic.
         "roofline": {"bound": "tensor", "achieved": fu_flops / max(fu_ms, 1e-9) / 1e9, "peak": peak, "unit": "TFLOP/s",
@@ -442,7 +473,7 @@ def main():
         "roofline_all_gemm": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "every tcgen05 launch of one utterance (gemm_tc / gemm_sk / gemm_ws* / resblock_fused), timed serially",
                      "launches_per_step": int(gn.value // 3), "ms_per_step": gemm_ms_per_step, "peak_source": pk_src,
-                     "algorithmic_flops_per_step": ALGO_FLOPS},
+                     "executed_flops_per_step": exec_flops, "nominal_flops_full_decode": ALGO_FLOPS},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # (1) e2e through the reference's literal call: wav FILE path in, .index FILE path in (pipeline.py:213-215 re-reads the

@@ -162,6 +162,14 @@ int rvcb_synth_create(const rvcb_synth_config* cfg, const rvcb_weights* w, rvcb_
 int rvcb_synth_infer(rvcb_synth* h, const float* d_phone, int T, int sid, const int64_t* d_pitch, const float* d_pitchf,
                      const float* d_noise_prior, const float* d_noise_src, int skip_head, int return_length,
                      int return_length2, float* d_wav_out, int* n_out, void* stream);
+/* The offline caller discards the x_pad context of every chunk (pipeline.py:241,295: audio1[t_pad_tgt : -t_pad_tgt]).  This entry returns
+ * exactly rvcb_synth_infer(...)[keep_head*upp : (keep_head+keep_length)*upp] -- bit for bit -- but runs the local parts of the model
+ * (flow: receptive field +-24 frames; decoder: +-10 frames) only over the kept frames plus margins; the TextEncoder (global attention) and
+ * the NSF sine phase (a running sum from frame 0) still cover all T frames.  d_noise_prior f32[inter, T] and d_noise_src f32[T*upp] are
+ * the FULL-length tensors of the untrimmed call; d_wav_out f32[keep_length*upp]. */
+int rvcb_synth_infer_keep(rvcb_synth* h, const float* d_phone, int T, int sid, const int64_t* d_pitch, const float* d_pitchf,
+                          const float* d_noise_prior, const float* d_noise_src, int keep_head, int keep_length, float* d_wav_out,
+                          int* n_out, void* stream);
 void rvcb_synth_destroy(rvcb_synth* h);
 
 /* ---- op-level entry for the unit tests: the implicit-GEMM engine -------------------------- */

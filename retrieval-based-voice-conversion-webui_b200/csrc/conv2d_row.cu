@@ -32,6 +32,7 @@ struct CRParams {
     float* out32; long ld32;
     __half* out16; long ld16;
     int relu;
+    int n_valid;                 // output channels actually present (bias entries, stored columns); 16 except for the 16 -> 3 head conv
 };
 
 __global__ void __launch_bounds__(CR_THREADS, 2)
@@ -116,7 +117,7 @@ conv2d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float bias[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bias[i] = __ldg(p.bias + i);
+        for (int i = 0; i < 16; ++i) bias[i] = i < p.n_valid ? __ldg(p.bias + i) : 0.f;
         int it = 0;
         for (int r = blockIdx.x; r < p.H; r += gridDim.x, ++it) {
             const int a = it & 1;
@@ -149,7 +150,9 @@ conv2d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<float4*>(p.out32 + px * p.ld32 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            if (p.out16) {
+            if (p.out16 && p.n_valid < 16) {               // narrow head (16 -> 3): a few scalar stores per pixel
+                for (int i = 0; i < p.n_valid; ++i) p.out16[px * p.ld16 + i] = __float2half_rn(v[i]);
+            } else if (p.out16) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
@@ -380,12 +383,14 @@ bool conv2d_row_try(const Conv2dRowArgs& a, cudaStream_t stream) {
     if (a.ldx % 8 || !al16(a.x) || !al16(a.w) || !a.bias) return false;
     if (a.res2 && (a.ldres2 % 4 || !al16(a.res2))) return false;
     if (a.out32 && (a.ld32 % 4 || !al16(a.out32))) return false;
-    if (a.out16 && (a.ld16 % 8 || !al16(a.out16))) return false;
+    const bool narrow = a.W == CR_W && a.cin == CR_C && a.cout < CR_C && a.cout >= 1 && a.out16 && !a.out32 && !a.res2;
+    if (a.out16 && !narrow && (a.ld16 % 8 || !al16(a.out16))) return false;
     if (!a.out32 && !a.out16) return false;
     CRParams p{};
     p.H = a.H; p.bias = a.bias; p.res2 = a.res2; p.ldres2 = a.ldres2; p.out32 = a.out32; p.ld32 = a.ld32; p.out16 = a.out16; p.ld16 = a.ld16;
     p.relu = a.relu ? 1 : 0;
-    if (!(a.W == CR_W && a.cin == CR_C && a.cout == CR_C)) {
+    p.n_valid = narrow ? a.cout : CR_C;
+    if (!(a.W == CR_W && a.cin == CR_C && (a.cout == CR_C || narrow))) {
         if (!tiles_on) return false;
         if (a.cin == 32 && a.cout == 32 && a.W == 64) { conv2d_tile_launch<32, 32, 64>(a, p, stream); return true; }
         if (a.cin == 64 && a.cout == 64 && a.W == 32) { conv2d_tile_launch<64, 64, 32>(a, p, stream); return true; }

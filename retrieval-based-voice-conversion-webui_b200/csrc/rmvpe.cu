@@ -670,13 +670,14 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     // ---- head: cnn 16->3, BiGRU, Linear + sigmoid ----
     __half* gru_in = ar.alloc<__half>((size_t)T * 384);
     {
+        const Conv2dRowArgs ra{cur16, 16, T, 128, 16, 3, h->cnn_w.d, h->cnn_w.rows, h->cnn_w.cols, h->cnn_b, false, nullptr, 0, nullptr, 0, gru_in, 3};
         GemmArgs g;
         g.A = cur16; g.lda = 16; g.a_rows = T; g.a_cols = 16; g.conv2d_W = 128;
         g.B = h->cnn_w.d; g.ldb = h->cnn_w.cols; g.b_rows = h->cnn_w.rows; g.b_cols = h->cnn_w.cols;
         g.M = T * 128; g.N = 3; g.block_k = 16;
         seg_conv2d_3x3(g, 16);
         g.bias = h->cnn_b; g.out16 = gru_in; g.ld16 = 3;
-        gemm(g, st);
+        if (!conv2d_row_try(ra, st)) gemm(g, st);
     }
     float* gi = ar.alloc<float>((size_t)T * 1536);
     {

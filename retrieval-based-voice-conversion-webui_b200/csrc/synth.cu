@@ -294,16 +294,28 @@ static rvcb_synth* synth_build(const rvcb_synth_config& c, const rvcb_weights& w
 
 static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, const long long* d_pitch, const float* d_pitchf,
                           const float* d_noise_prior, const float* d_noise_src, int skip_head, int return_length, int return_length2,
-                          float* d_wav_out, int* n_out, cudaStream_t st) {
+                          float* d_wav_out, int* n_out, cudaStream_t st, int keep_head = -1, int keep_length = -1) {
     const rvcb_synth_config& c = h->cfg;
     const int H = c.hidden_channels, F = c.filter_channels, I = c.inter_channels, heads = c.n_heads, kc = h->kc, HP = h->HP;
     const int upp = h->upp;
     RVCB_CHECK(T >= 1 && sid >= 0 && sid < c.spk_embed_dim, "synth: bad T or sid");
     const bool rt = skip_head >= 0 && return_length >= 0;
-    const int flow_head = rt ? std::max(skip_head - 24, 0) : 0;
-    const int dec_head = rt ? skip_head - flow_head : 0;
-    const int Tf = T - flow_head;                        // frames through the flow
-    const int Td = rt ? return_length : T;               // frames into the decoder
+    // "keep" mode (offline utterances): the caller discards everything outside frames [keep_head, keep_head + keep_length) -- the
+    // x_pad context of pipeline.py:241,295.  TextEncoder attention is global and runs over all T frames; the flow (receptive field
+    // +-24 frames, the reference's own constant at synthesizers.py:172) and the decoder (+-10 frames: conv_pre 3 + the resblock /
+    // transposed-conv halos of the four stages) are local, so they run over the kept frames plus margins only.  Every kept sample
+    // sees exactly the operands it sees in the full computation (the NSF sine phase is still accumulated from frame 0, the noise
+    // tensors are the full-length ones): the kept output is bit-identical to infer(...)[keep_head*upp : (keep_head+keep_length)*upp].
+    const bool keep = !rt && keep_head >= 0 && keep_length >= 1;
+    constexpr int kDecMargin = 16, kFlowMargin = 24;
+    RVCB_CHECK(!keep || (keep_head + keep_length <= T && return_length2 < 0), "synth: bad keep_head/keep_length");
+    const int ds = keep ? std::max(keep_head - kDecMargin, 0) : 0;                         // first decoder frame
+    const int de = keep ? std::min(keep_head + keep_length + kDecMargin, T) : T;            // one past the last decoder frame
+    const int flow_head = rt ? std::max(skip_head - 24, 0) : (keep ? std::max(ds - kFlowMargin, 0) : 0);
+    const int flow_end = keep ? std::min(de + kFlowMargin, T) : T;
+    const int dec_head = rt ? skip_head - flow_head : ds - flow_head;
+    const int Tf = flow_end - flow_head;                 // frames through the flow
+    const int Td = rt ? return_length : de - ds;         // frames into the decoder
     const int Tn = (return_length2 >= 0) ? return_length2 : Td;   // decoder frames after formant resize
     RVCB_CHECK(Tf >= 1 && Td >= 1 && dec_head + Td <= Tf && Tn >= 1, "synth: bad skip_head/return_length");
     const int Tp = round_up(T, 8);
@@ -314,7 +326,7 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     need += rnd((size_t)T * 2 * heads * HP * 2) + rnd((size_t)H * Tp * 2) + rnd((size_t)heads * T * Tp * 4) + rnd((size_t)heads * T * Tp * 2);
     need += rnd((size_t)heads * T * 32 * 4) + rnd((size_t)heads * T * 64 * 2) + rnd((size_t)T * F * 2) + rnd((size_t)T * 2 * I * 4);
     need += 6 * rnd((size_t)Tf * H * 4) + 4 * rnd((size_t)Tf * H * 2);
-    need += 2 * rnd((size_t)Tn * upp * 4) + rnd((size_t)Tn * (c.upsample_initial_channel + h->stages[0].Mp) * 2) + 2 * rnd((size_t)Tn * I * 4);
+    need += (keep ? 2 * rnd((size_t)T * upp * 4) + rnd((size_t)T * 4 + 64) : 0) + 2 * rnd((size_t)Tn * upp * 4) + rnd((size_t)Tn * (c.upsample_initial_channel + h->stages[0].Mp) * 2) + 2 * rnd((size_t)Tn * I * 4);
     size_t carry_e = 0;      // halves per carry buffer: widest [T_in, C_in + Mp] input of stages 1.. and the last stage's output
     {
         size_t mx = 0;
@@ -450,7 +462,8 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     // ================= prior sample + flow^-1 (synthesizers.py:187-189, residuals.py:210-235) =================
     float* zA = ar.alloc<float>((size_t)Tf * I);
     float* zB = ar.alloc<float>((size_t)Tf * I);
-    prior_sample(stats32, d_noise_prior, Tf, Tf, I, zA, st);
+    // keep mode: the prior noise is the full-length [inter, T] tensor, read from frame flow_head on
+    prior_sample(stats32, keep ? d_noise_prior + flow_head : d_noise_prior, keep ? T : Tf, Tf, I, zA, st);
     const int half = I / 2;
     const float* gvec = h->emb_g + (size_t)sid * c.gin_channels;
     float* cbias = ar.alloc<float>((size_t)4 * 3 * 2 * H);
@@ -506,7 +519,14 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
     const float* z = zin + (size_t)dec_head * I;          // [Td, I]
     // ================= NSF-HiFi-GAN (nsf.py:145-191) =================
     float* har = nullptr;
-    if (h->use_f0) {
+    if (h->use_f0 && keep) {
+        // the sine phase is a running sum over ALL frames (generators.py:166-177): build the source for the whole utterance
+        // (one elementwise kernel over T * upp samples) and hand the decoder its slice
+        float* phase = ar.alloc<float>((size_t)T + 8);
+        float* har_full = ar.alloc<float>((size_t)T * upp);
+        sine_source(d_pitchf, T, upp, c.sr, d_noise_src, h->lin_w, h->lin_b, phase, har_full, st);
+        har = har_full + (size_t)ds * upp;
+    } else if (h->use_f0) {
         const float* pf = d_pitchf + (rt ? skip_head : 0);
         float* phase = ar.alloc<float>((size_t)Td + 8);
         har = ar.alloc<float>((size_t)Td * upp);
@@ -627,6 +647,14 @@ static void synth_forward(rvcb_synth* h, const float* d_phone, int T, int sid, c
         carry16 = next16;
         Tt = Tout;
     }
+    if (keep) {
+        float* wav_tmp = ar.alloc<float>((size_t)Tt);
+        conv_post_tanh(carry16, Tt, h->stages.back().cout, h->conv_post_w, h->conv_post_k, wav_tmp, st);
+        CUDA_CHECK(cudaMemcpyAsync(d_wav_out, wav_tmp + (size_t)(keep_head - ds) * upp, sizeof(float) * (size_t)keep_length * upp,
+                                   cudaMemcpyDeviceToDevice, st));
+        if (n_out) *n_out = keep_length * upp;
+        return;
+    }
     conv_post_tanh(carry16, Tt, h->stages.back().cout, h->conv_post_w, h->conv_post_k, d_wav_out, st);
     if (n_out) *n_out = Tt;
 }
@@ -648,6 +676,18 @@ int rvcb_synth_infer(rvcb_synth* h, const float* d_phone, int T, int sid, const 
     RVCB_CHECK(!h->use_f0 || (d_pitch && d_pitchf && d_noise_src), "f0 model: pitch, pitchf and the source noise are required");
     synth_forward(h, d_phone, T, sid, (const long long*)d_pitch, d_pitchf, d_noise_prior, d_noise_src, skip_head, return_length,
                   return_length2, d_wav_out, n_out, (cudaStream_t)stream);
+    RVCB_API_END
+}
+
+int rvcb_synth_infer_keep(rvcb_synth* h, const float* d_phone, int T, int sid, const int64_t* d_pitch, const float* d_pitchf,
+                          const float* d_noise_prior, const float* d_noise_src, int keep_head, int keep_length, float* d_wav_out, int* n_out,
+                          void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(h && d_phone && d_noise_prior && d_wav_out, "null argument");
+    RVCB_CHECK(!h->use_f0 || (d_pitch && d_pitchf && d_noise_src), "f0 model: pitch, pitchf and the source noise are required");
+    RVCB_CHECK(keep_head >= 0 && keep_length >= 1 && keep_head + keep_length <= T, "bad keep_head / keep_length");
+    synth_forward(h, d_phone, T, sid, (const long long*)d_pitch, d_pitchf, d_noise_prior, d_noise_src, -1, -1, -1, d_wav_out, n_out,
+                  (cudaStream_t)stream, keep_head, keep_length);
     RVCB_API_END
 }
 

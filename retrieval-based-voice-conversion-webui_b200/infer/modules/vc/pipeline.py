@@ -108,7 +108,10 @@ class Pipeline(object):
         """Reference signature (pipeline.py:76): returns the chunk's waveform as a host float32 array."""
         return self._vc_dev(model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect).cpu().numpy()
 
-    def _vc_dev(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
+    def _vc_dev(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect, trim=False):
+        """Device form of ``vc``.  trim=True returns the chunk WITHOUT its x_pad context, i.e. what the callers keep after
+        ``audio1[t_pad_tgt : -t_pad_tgt]`` (pipeline.py:295): the synthesizer then runs its local stages (flow, decoder) only over
+        the kept frames plus their receptive-field margins -- the kept samples are bit-identical (rvcb_synth_infer_keep)."""
         t0 = time()
         if self._prefetched is not None and self._prefetched[0] is audio0:
             _, f, f_raw, ev = self._prefetched          # computed on the side stream while RMVPE was running
@@ -141,8 +144,18 @@ class Pipeline(object):
                 phone = phone[: pitch.shape[1]]
                 T = phone.shape[0]
             host_ok = getattr(net_g, "accepts_host_scalars", False)      # a device tensor here costs a stream sync (.item())
-            audio1 = net_g.infer(phone.unsqueeze(0), torch.tensor([T]) if host_ok else torch.tensor([T], device=self.device), sid,
-                                 pitch=None if pitch is None else pitch[:, :T], pitchf=None if pitchf is None else pitchf[:, :T])[0, 0]
+            lengths = torch.tensor([T]) if host_ok else torch.tensor([T], device=self.device)
+            pad_f = self.t_pad_tgt // getattr(net_g, "upp", 0) if getattr(net_g, "upp", 0) else 0
+            can_keep = (trim and host_ok and pad_f > 0 and T > 2 * pad_f and os.environ.get("RVCB_TRIM", "1") != "0"
+                        and pad_f * net_g.upp == self.t_pad_tgt)
+            if can_keep:
+                audio1 = net_g.infer(phone.unsqueeze(0), lengths, sid, pitch=None if pitch is None else pitch[:, :T],
+                                     pitchf=None if pitchf is None else pitchf[:, :T], keep_head=pad_f, keep_length=T - 2 * pad_f)[0, 0]
+            else:
+                audio1 = net_g.infer(phone.unsqueeze(0), lengths, sid, pitch=None if pitch is None else pitch[:, :T],
+                                     pitchf=None if pitchf is None else pitchf[:, :T])[0, 0]
+                if trim:
+                    audio1 = audio1[self.t_pad_tgt: -self.t_pad_tgt]
         t2 = time()
         times[0] += t1 - t0
         times[2] += t2 - t1
@@ -212,9 +225,8 @@ class Pipeline(object):
             if not capturing:
                 audio_pad.record_stream(self._side)
             self._prefetched = (audio_pad, f, f_raw, ev)
-        out = self._vc_dev(model, net_g, sid, audio_pad, pitch, pitchf, times, index, big_npy, index_rate, version, protect)
-        out = out[self.t_pad_tgt: -self.t_pad_tgt].contiguous()
-        out = engine.post_mix(out, tgt_sr, a16, rms_mix_rate)
+        out = self._vc_dev(model, net_g, sid, audio_pad, pitch, pitchf, times, index, big_npy, index_rate, version, protect, trim=True)
+        out = engine.post_mix(out.contiguous(), tgt_sr, a16, rms_mix_rate)
         return engine.f32_to_i16(out) if as_int16 else out
 
     def _pipeline_single_dev(self, model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
@@ -333,12 +345,12 @@ class Pipeline(object):
             audio_opt.append(self._vc_dev(model, net_g, sid, audio_pad[s: t + self.t_pad2 + W],
                                      pitch[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
                                      pitchf[:, s // W: (t + self.t_pad2) // W] if if_f0 else None,
-                                     times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
+                                     times, index, big_npy, index_rate, version, protect, trim=True))
             s = t
         audio_opt.append(self._vc_dev(model, net_g, sid, audio_pad if t is None else audio_pad[t:],
                                  (pitch[:, t // W:] if t is not None else pitch) if if_f0 else None,
                                  (pitchf[:, t // W:] if t is not None else pitchf) if if_f0 else None,
-                                 times, index, big_npy, index_rate, version, protect)[self.t_pad_tgt: -self.t_pad_tgt])
+                                 times, index, big_npy, index_rate, version, protect, trim=True))
         audio_dev = audio_opt[0] if len(audio_opt) == 1 else torch.cat(audio_opt)
         if not (tgt_sr != resample_sr >= 16000):
             # RMS-envelope mix + peak normalisation on the device (pipeline.py:349-360), then ONE D2H copy of the result

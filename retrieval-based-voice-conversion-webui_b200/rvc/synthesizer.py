@@ -51,7 +51,9 @@ class SynthesizerB200:
     @torch.no_grad()
     def infer(self, phone: torch.Tensor, phone_lengths: torch.Tensor, sid: torch.Tensor, pitch: Optional[torch.Tensor] = None,
               pitchf: Optional[torch.Tensor] = None, skip_head: Optional[int] = None, return_length: Optional[int] = None,
-              return_length2: Optional[int] = None) -> torch.Tensor:
+              return_length2: Optional[int] = None, keep_head: Optional[int] = None, keep_length: Optional[int] = None) -> torch.Tensor:
+        """keep_head / keep_length (not in the reference signature; used by the drop-in Pipeline): return only
+        ``infer(...)[:, :, keep_head*upp : (keep_head+keep_length)*upp]`` -- bit for bit, see rvcb_synth_infer_keep."""
         if phone.dim() != 3:
             raise ValueError("phone must be [B, T, C]")
         if phone.shape[0] != 1:
@@ -88,6 +90,12 @@ class SynthesizerB200:
             if self.use_f0:
                 torch.rand(1, 1, 1, device=self.device)
                 n2 = torch.randn(1, Td * self.upp, 1, device=self.device)
+        if keep_head is not None and keep_length is not None and skip_head is None:
+            out = self._synth.infer_keep(phone[0].to(self.device), int(sid.reshape(-1)[0]),
+                                         pitch.reshape(-1)[:T].to(self.device) if self.use_f0 else None,
+                                         pitchf.reshape(-1)[:T].to(self.device) if self.use_f0 else None, n1.to(self.device),
+                                         None if n2 is None else n2.to(self.device), int(keep_head), int(keep_length))
+            return out.view(1, 1, -1)
         out = self._synth.infer(phone[0].to(self.device), int(sid.reshape(-1)[0]),
                                 pitch.reshape(-1)[:T].to(self.device) if self.use_f0 else None,
                                 pitchf.reshape(-1)[:T].to(self.device) if self.use_f0 else None, n1.to(self.device),

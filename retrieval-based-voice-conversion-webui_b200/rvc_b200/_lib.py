@@ -92,6 +92,7 @@ SIGNATURES = {
     "rvcb_rmvpe_destroy": (None, [_P]),
     "rvcb_synth_create": (_I, [C.POINTER(SynthConfig), _P, C.POINTER(_P)]),
     "rvcb_synth_infer": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, C.POINTER(_I), _P]),
+    "rvcb_synth_infer_keep": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, C.POINTER(_I), _P]),
     "rvcb_synth_destroy": (None, [_P]),
     "rvcb_op_gemm": (_I, [C.POINTER(GemmDesc), _I, _P]),
 }

@@ -383,6 +383,24 @@ class Synth:
                                                -1 if return_length2 is None else int(return_length2), _p(out), C.byref(n), _stream_ptr()))
         return out[: n.value]
 
+    def infer_keep(self, phone: torch.Tensor, sid: int, pitch: Optional[torch.Tensor], pitchf: Optional[torch.Tensor], noise_prior: torch.Tensor,
+                   noise_src: Optional[torch.Tensor], keep_head: int, keep_length: int) -> torch.Tensor:
+        """``infer(...)[keep_head*upp : (keep_head+keep_length)*upp]`` bit for bit, with the flow / decoder restricted to the kept frames
+        plus their receptive-field margins (rvcb_synth_infer_keep).  noise tensors are the full-length ones of ``infer``."""
+        phone = _chk_dev(phone.reshape(-1, phone.shape[-1]), torch.float32, "phone")
+        T = phone.shape[0]
+        pitch = None if pitch is None else _chk_dev(pitch.reshape(-1), torch.int64, "pitch")
+        pitchf = None if pitchf is None else _chk_dev(pitchf.reshape(-1), torch.float32, "pitchf")
+        noise_prior = _chk_dev(noise_prior.reshape(self.inter, -1), torch.float32, "noise_prior")
+        noise_src = None if noise_src is None else _chk_dev(noise_src.reshape(-1), torch.float32, "noise_src")
+        if noise_prior.shape[1] != T or (noise_src is not None and noise_src.numel() != T * self.upp):
+            raise RuntimeError("infer_keep takes the full-length noise tensors of the untrimmed call")
+        out = torch.empty(int(keep_length) * self.upp, device=phone.device, dtype=torch.float32)
+        n = C.c_int(0)
+        _lib.check(_lib.lib().rvcb_synth_infer_keep(self.h, _p(phone), T, int(sid), _p(pitch), _p(pitchf), _p(noise_prior), _p(noise_src),
+                                                    int(keep_head), int(keep_length), _p(out), C.byref(n), _stream_ptr()))
+        return out[: n.value]
+
     def __del__(self):
         try:
             if self.h:

@@ -132,3 +132,28 @@ def test_synth_other_decoder_schedules(name):
     out = m.infer(phone[0].cuda(), 5, pitch[0].cuda(), pitchf[0].cuda(), n1[0].cuda(), n2.reshape(-1).cuda()).cpu()
     assert out.shape == ref.shape == (T * upp,)
     assert (out - ref).abs().max().item() <= 1e-3, (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("f0", [1, 0])
+def test_keep_mode_is_bit_identical_to_the_slice_of_the_full_decode(f0):
+    """rvcb_synth_infer_keep: the flow and the decoder run over the kept frames plus their receptive-field margins only; the kept
+    samples must equal infer(...)[keep_head*upp : (keep_head+keep_length)*upp] BIT FOR BIT (same noise tensors, sine phase still
+    accumulated from frame 0).  This is what the offline pipeline uses to skip the x_pad context it discards anyway."""
+    from oracle import weights as OW
+    from rvc_b200.engine import Synth
+    cfg = OW.V2_48K_CONFIG
+    w = OW.synth_weights(1234) if f0 else {k: v for k, v in OW.synth_weights(1234).items() if "emb_pitch" not in k and "noise_convs" not in k and "m_source" not in k}
+    syn = Synth(w, cfg, 768)
+    g = torch.Generator().manual_seed(5)
+    for T, kh, kl in ((420, 100, 220), (300, 40, 200), (260, 0, 260), (500, 300, 150)):
+        phone = (torch.randn(T, 768, generator=g) * 0.5).cuda()
+        pitch = torch.randint(1, 255, (T,), generator=g).cuda() if f0 else None
+        pitchf = (torch.rand(T, generator=g) * 300 + 80).cuda() if f0 else None
+        if f0:
+            pitchf[T // 3: T // 3 + 20] = 0
+        n1 = torch.randn(192, T, generator=g).cuda()
+        n2 = torch.randn(T * 480, generator=g).cuda() if f0 else None
+        full = syn.infer(phone, 0, pitch, pitchf, n1, n2)
+        kept = syn.infer_keep(phone, 0, pitch, pitchf, n1, n2, kh, kl)
+        assert kept.shape == (kl * 480,)
+        assert torch.equal(kept, full[kh * 480: (kh + kl) * 480]), (T, kh, kl, (kept - full[kh * 480: (kh + kl) * 480]).abs().max().item())
