@@ -129,6 +129,27 @@ int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream);
 int rvcb_rt_tail(float* d_infer, int n, const float* d_input, int zc, float rms_mix_rate, float* d_sola_buffer, int block_frame,
                  int sola_buffer_frame, int sola_search_frame, float* d_out, float* d_scratch, int* d_offset, void* stream);
 
+/* ---- realtime noise gate and resamplers around RVC.infer, per block, on the device -------------------------------------
+ * rvcb_torchgate_*  replaces: infer/modules/gui/torchgate.py TorchGate.__init__ :33-70 / forward :217-280 (the torch.stft /
+ * torch.istft branch; stationary mask :128-178 with or without a noise reference, non-stationary mask :180-215, mask smoothing
+ * :253-258) as used at gui.py:869-871 (n_fft = 4 * zc, prop_decrease 0.9), :974-990 (input) and :1015-1023 (output).  fp32.
+ * h_filter: HOST f32[filter_rows, filter_cols] smoothing filter of _generate_mask_smoothing_filter :72-126 (rows = frequency,
+ * odd sizes; 0 x 0 = none).  apply: d_x f32[n], d_xn f32[n_noise] noise reference (nullable: the signal's own statistics),
+ * d_y f32[rvcb_torchgate_out_len(h, n)] = hop * (n / hop) samples (torch.istft's length); batch 1 (the GUI's unsqueeze(0)). */
+typedef struct rvcb_torchgate rvcb_torchgate;
+int rvcb_torchgate_create(int sr, int n_fft, int hop, int nonstationary, float n_std_thresh_stationary, float n_thresh_nonstationary,
+                          float temp_coeff_nonstationary, int n_movemean_nonstationary, float prop_decrease, const float* h_filter,
+                          int filter_rows, int filter_cols, rvcb_torchgate** out);
+int64_t rvcb_torchgate_out_len(const rvcb_torchgate* h, int64_t n);
+int rvcb_torchgate_apply(rvcb_torchgate* h, const float* d_x, int64_t n, const float* d_xn, int64_t n_noise, float* d_y, void* stream);
+void rvcb_torchgate_destroy(rvcb_torchgate* h);
+/* replaces: torchaudio.transforms.Resample.forward (gui.py:851-866 resampler / resampler2, applied at gui.py:991-1000, :1008-1009):
+ * out[i * up + p] = sum_k kernel[p, k] * xpad[i * down + k], xpad = x with `width` zeros on the left; d_kernel f32[up, kernel_width]
+ * is the windowed-sinc table of torchaudio's _get_sinc_resample_kernel (built by the host mirror with torchaudio's own formula),
+ * up / down = new / orig rate over their gcd, n_out = ceil(up * n / down). */
+int rvcb_resample_sinc(const float* d_x, int64_t n, const float* d_kernel, int up, int down, int kernel_width, int width, float* d_out,
+                       int64_t n_out, void* stream);
+
 /* ---- f0 post-processing on the device (no host round trip between RMVPE and the synthesizer) ----
  * replaces: F0Predictor._resize_f0 + _interpolate_f0 (rvc/f0/f0.py:31-78) and post_process (rvc/f0/gen.py:10-41, without
  * a manual f0 curve), float64 with numpy's operation order.  d_f0 f32[n_frames] (Hz, 0 = unvoiced) -> d_pitch i64[p_len]

@@ -1,1 +1,3 @@
 from .realtime_tail import RealtimeTail  # noqa: F401
+from .torchgate import TorchGate  # noqa: F401
+from .resample import Resample  # noqa: F401

@@ -230,6 +230,73 @@ def rt_tail(infer_wav: torch.Tensor, input_wav: Optional[torch.Tensor], zc: int,
     return (out, off) if want_offset else out
 
 
+class TorchGateHandle:
+    """rvcb_torchgate_*: the realtime GUI's spectral gate on the device (fp32).  ``filt``: HOST float32 [rows, cols] smoothing filter
+    or None."""
+
+    def __init__(self, sr: int, n_fft: int, hop: int, nonstationary: bool, n_std_thresh_stationary: float, n_thresh_nonstationary: float,
+                 temp_coeff_nonstationary: float, n_movemean_nonstationary: int, prop_decrease: float, filt: Optional[torch.Tensor],
+                 device_index: int = 0):
+        _lib.init(device_index)
+        self.h = C.c_void_p()
+        f = None if filt is None else filt.detach().to("cpu", torch.float32).contiguous()
+        _lib.check(_lib.lib().rvcb_torchgate_create(int(sr), int(n_fft), int(hop), int(bool(nonstationary)), float(n_std_thresh_stationary),
+                                                    float(n_thresh_nonstationary), float(temp_coeff_nonstationary), int(n_movemean_nonstationary),
+                                                    float(prop_decrease), None if f is None else f.data_ptr(), 0 if f is None else f.shape[0],
+                                                    0 if f is None else f.shape[1], C.byref(self.h)))
+        self.hop = int(hop)
+
+    def apply(self, x: torch.Tensor, xn: Optional[torch.Tensor]) -> torch.Tensor:
+        x = _chk_dev(x.reshape(-1), torch.float32, "x")
+        n = x.numel()
+        noise = None if xn is None else _chk_dev(xn.reshape(-1), torch.float32, "xn")
+        y = torch.empty(self.hop * (n // self.hop), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().rvcb_torchgate_apply(self.h, _p(x), n, _p(noise), 0 if noise is None else noise.numel(), _p(y), _stream_ptr()))
+        return y
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rvcb_torchgate_destroy(self.h)
+        except Exception:
+            pass
+
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99, dtype=torch.float32):
+    """The [new/gcd, 2*width + orig/gcd] windowed-sinc table of torchaudio.transforms.Resample(orig, new, dtype=dtype) with its
+    defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99), same operation order as torchaudio's
+    _get_sinc_resample_kernel so the table is equal to the one gui.py:851-866 builds.  Returns (kernel [up, kw] CPU, width, up, down)."""
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx_dtype = dtype if dtype is not None else torch.float64
+    idx = torch.arange(-width, width + orig, dtype=idx_dtype)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=dtype)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    if dtype is None:
+        kernels = kernels.to(dtype=torch.float32)
+    return kernels[:, 0].contiguous().float(), width, new, orig
+
+
+def sinc_resample(x: torch.Tensor, kernel: torch.Tensor, width: int, up: int, down: int) -> torch.Tensor:
+    """rvcb_resample_sinc: x f32[n] (device) -> f32[ceil(up * n / down)]; ``kernel`` f32[up, kw] on the device."""
+    x = _chk_dev(x.reshape(-1), torch.float32, "x")
+    k = _chk_dev(kernel, torch.float32, "kernel")
+    n = x.numel()
+    n_out = -((-up * n) // down)
+    out = torch.empty(n_out, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().rvcb_resample_sinc(_p(x), n, _p(k), int(up), int(down), int(k.shape[1]), int(width), _p(out), n_out, _stream_ptr()))
+    return out
+
+
 def host_filtfilt(b: np.ndarray, a: np.ndarray, zi: np.ndarray, x: np.ndarray) -> np.ndarray:
     """scipy.signal.filtfilt(b, a, x) (defaults) on the host, in C (rvcb_host_filtfilt); float32 / float64 in, float64 out."""
     b = np.ascontiguousarray(b, dtype=np.float64); a = np.ascontiguousarray(a, dtype=np.float64)

@@ -104,7 +104,50 @@ def hubert():
     np.savez_compressed(os.path.join(OUT, "hubert_hf_0p5s.npz"), layer9=hs[9][0].numpy(), layer12=hs[12][0].numpy())
 
 
+def torchgate_inputs(seed, n, n_noise, sr):
+    """Seeded test signal shared by this script and tests/: a gliding harmonic tone with an onset + white noise floor."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n_noise) / sr
+    tone = sum(torch.sin(2 * math.pi * (180.0 + 40.0 * t) * h * t) / h for h in (1, 2, 3, 5))
+    env = ((t * 3.0) % 1.0 < 0.6).float()
+    xn = 0.3 * tone * env + 0.02 * torch.randn(n_noise, generator=g)
+    return xn[-n:].clone()[None], xn[None]
+
+
+def torchgate():
+    """The reference's OWN TorchGate (infer/modules/gui/torchgate.py) on seeded inputs.  Its module imports rvc.f0.stft, whose
+    top-level `from librosa.util import pad_center` is only used by the DirectML STFT class the CPU branch never builds:
+    librosa is absent here, so a stub module supplies that one name."""
+    import types
+    if "librosa" not in sys.modules:
+        lib = types.ModuleType("librosa"); util = types.ModuleType("librosa.util")
+        util.pad_center = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        lib.util = util
+        sys.modules["librosa"] = lib; sys.modules["librosa.util"] = util
+    # oracle.weights put the product package (which mirrors the `infer.*` names as a regular package) on sys.path: hide it
+    saved_path, saved_mods = sys.path[:], {k: sys.modules.pop(k) for k in list(sys.modules) if k == "infer" or k.startswith("infer.")}
+    sys.path[:] = ["/root/reference"] + [p for p in sys.path if "webui_b200" not in p]
+    try:
+        from infer.modules.gui.torchgate import TorchGate
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "infer" or k.startswith("infer.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+    assert "/root/reference" in TorchGate.forward.__code__.co_filename
+    out = {}
+    # (a) the realtime GUI's instance (gui.py:869-871): sr = 48 kHz, n_fft = 4 * zc = 1920, prop_decrease 0.9, noise reference given
+    x, xn = torchgate_inputs(21, 9600, 48000, 48000)
+    out["rt_y"] = TorchGate(sr=48000, n_fft=1920, prop_decrease=0.9)(x, xn)[0].numpy()
+    out["rt_y_self"] = TorchGate(sr=48000, n_fft=1920, prop_decrease=0.9)(x)[0].numpy()           # xn = None: own statistics
+    # (b) class defaults at 16 kHz (n_fft 1024, hop 256), stationary and non-stationary
+    x, xn = torchgate_inputs(22, 8192, 32000, 16000)
+    out["d16_y"] = TorchGate(sr=16000)(x, xn)[0].numpy()
+    out["d16_ns_y"] = TorchGate(sr=16000, nonstationary=True, prop_decrease=0.8)(x)[0].numpy()
+    np.savez_compressed(os.path.join(OUT, "torchgate.npz"), **out)
+
+
 if __name__ == "__main__":
-    synth(); rmvpe(); f0_fixtures(); hubert()
+    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,5 +1,6 @@
 """CPU: the oracle against golden vectors produced by the REFERENCE's own modules (tests/golden/make_golden.py) and the
 reference's own fixtures (infer/modules/vc/lgdsng.npz, logs/mute/2a_f0, 2b-f0nsf)."""
+import math
 import os
 
 import numpy as np
@@ -93,3 +94,34 @@ def test_ivf_oracle_against_an_independent_knn():
         assert set(I[qi, :k].tolist()) == set(j[:k].tolist()), qi
         checked += 1
     assert checked >= 50
+
+
+def test_torchgate_oracle_matches_reference_golden():
+    """oracle/torchgate.py vs the outputs of the reference's own TorchGate class (both on CPU torch.stft: bit-equal)."""
+    import math
+    from oracle import torchgate as OT
+    z = np.load(os.path.join(G, "torchgate.npz"))
+
+    def inputs(seed, n, n_noise, sr):
+        g = torch.Generator().manual_seed(seed)
+        t = torch.arange(n_noise) / sr
+        tone = sum(torch.sin(2 * math.pi * (180.0 + 40.0 * t) * h * t) / h for h in (1, 2, 3, 5))
+        env = ((t * 3.0) % 1.0 < 0.6).float()
+        xn = 0.3 * tone * env + 0.02 * torch.randn(n_noise, generator=g)
+        return xn[-n:].clone()[None], xn[None]
+    x, xn = inputs(21, 9600, 48000, 48000)
+    assert np.abs(OT.torchgate(x, xn, 48000, 1920, prop_decrease=0.9)[0].numpy() - z["rt_y"]).max() <= 1e-7
+    assert np.abs(OT.torchgate(x, None, 48000, 1920, prop_decrease=0.9)[0].numpy() - z["rt_y_self"]).max() <= 1e-7
+    x, xn = inputs(22, 8192, 32000, 16000)
+    assert np.abs(OT.torchgate(x, xn, 16000)[0].numpy() - z["d16_y"]).max() <= 1e-7
+    assert np.abs(OT.torchgate(x, None, 16000, nonstationary=True, prop_decrease=0.8)[0].numpy() - z["d16_ns_y"]).max() <= 1e-7
+
+
+def test_resample_table_equals_torchaudio():
+    """The product's windowed-sinc table (engine.sinc_resample_kernel) is torchaudio's, entry for entry."""
+    import torchaudio.transforms as tat
+    from rvc_b200 import engine
+    for o, n in ((48000, 16000), (16000, 48000), (40000, 48000), (44100, 16000), (32000, 48000)):
+        k, w, up, down = engine.sinc_resample_kernel(o, n)
+        r = tat.Resample(o, n, dtype=torch.float32)
+        assert torch.equal(k, r.kernel[:, 0]) and w == r.width and (up, down) == (n // math.gcd(o, n), o // math.gcd(o, n))
