@@ -409,6 +409,29 @@ def main():
         realtime = {"config": "configs[2]: 160 ms blocks, 43520-sample 16 kHz window, skip_head 250, return_length 21, v2/48k + RMVPE + 100k index",
                     "blocks": int(nblk), "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "max_ms": float(lat.max()),
                     "block_period_ms": 160.0, "what": "rtrvc.RVC.infer + RealtimeTail.process (envelope mix + SOLA) + D2H of the 7680-sample block, wall clock"}
+        # the whole callback as one object: host block in -> host block out (gui.py:940-1090), one H2D + one graph + one D2H
+        try:
+            from infer.modules.gui import RealtimeBlock
+            mic = SY.synth_voice(0.16 * (nblk + nwarm) + 0.1, sr=48000, seed=7).numpy()
+
+            def callback_latency(**kw):
+                blk = RealtimeBlock(rt, samplerate=48000, block_time=0.16, crossfade_time=0.05, extra_time=2.5, device=str(dev), **kw)
+                ls = []
+                for b in range(nblk + nwarm):
+                    ind = mic[b * blk.block_frame: (b + 1) * blk.block_frame]
+                    t0 = time.perf_counter()
+                    blk.process(ind)
+                    ls.append((time.perf_counter() - t0) * 1e3)
+                ls = np.array(ls[nwarm:])
+                return {"p50_ms": float(np.percentile(ls, 50)), "p99_ms": float(np.percentile(ls, 99)), "max_ms": float(ls.max())}
+            realtime["callback"] = {
+                "what": "RealtimeBlock.process: host numpy block in -> host numpy block out (input ring, 48k->16k resampler, RVC.infer, "
+                        "envelope mix, SOLA as ONE CUDA graph + H2D + D2H), wall clock",
+                "gui_defaults": callback_latency(rms_mix_rate=0.0),
+                "with_input_and_output_noise_gate": callback_latency(rms_mix_rate=0.0, I_noise_reduce=True, O_noise_reduce=True)}
+        except Exception as e:
+            realtime["callback"] = {"error": repr(e)[:300]}
+            torch.cuda.synchronize()
         del rt, tail
 
     # ---- roofline of the dominant kernel family (gemm_tc): live CUDA events around every launch of one step set ----

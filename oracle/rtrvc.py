@@ -13,8 +13,13 @@ Reference sites restated:
       volume-envelope mix  (librosa.feature.rms(frame 4*zc, hop zc), align_corners interpolation)   gui.py:1024-1056
       SOLA offset search + cross-fade + buffer update                                             gui.py:1057-1087
   fade windows sin^2                                   gui.py:841-855
-librosa.feature.rms is restated (centred frames, zero padding) as in oracle/pipeline.py; TorchGate noise reduction
-(gui.py:1015-1023, off by default) and the phase-vocoder cross-fade (use_pv, off by default) are not restated.
+  whole device side of the audio callback (``OracleCallback``)                                  gui.py:783-871, 940-1090
+      response-threshold gate on the host block (librosa rms, zero the quiet zc-segments)          gui.py:951-966
+      input ring shifts, input TorchGate + cross-fade with nr_buffer, resample to 16 kHz          gui.py:967-1000
+      RVC.infer, resampler2, output TorchGate against output_buffer                               gui.py:1002-1023
+librosa.feature.rms is restated (centred frames, zero padding) as in oracle/pipeline.py; TorchGate is oracle/torchgate.py (pinned
+to the reference class); the resamplers are torchaudio.transforms.Resample itself (the library the reference calls).  The
+phase-vocoder cross-fade (use_pv, off by default) is not restated.
 The formant-shift resampling branch (rtrvc.py:251-260, torchaudio Resample) is outside the oracle: tests use formant = 0.
 """
 from __future__ import annotations
@@ -118,3 +123,82 @@ class SolaTail:
         infer_wav[: self.sola_buffer_frame] += self.sola_buffer * self.fade_out
         self.sola_buffer[:] = infer_wav[self.block_frame: self.block_frame + self.sola_buffer_frame]
         return infer_wav[: self.block_frame].clone(), sola_offset
+
+
+class OracleCallback:
+    """gui.py:783-871 (block geometry + state) and :940-1090 (one block), for ``function == "vc"``, mono input, use_pv off.
+    ``rvc``: an OracleRVC whose tgt_sr may differ from ``samplerate`` (then resampler2 runs)."""
+
+    def __init__(self, rvc: OracleRVC, samplerate: int = 48000, block_time: float = 0.25, crossfade_time: float = 0.05,
+                 extra_time: float = 2.5, I_noise_reduce: bool = False, O_noise_reduce: bool = False, rms_mix_rate: float = 1.0,
+                 threhold: float = -60.0):
+        import torchaudio.transforms as tat
+        from . import torchgate as OT
+        self.rvc, self.sr = rvc, samplerate
+        self.I_noise_reduce, self.O_noise_reduce, self.rms_mix_rate, self.threhold = I_noise_reduce, O_noise_reduce, rms_mix_rate, threhold
+        zc = self.zc = samplerate // 100
+        self.block_frame = int(np.round(block_time * samplerate / zc)) * zc
+        self.block_frame_16k = 160 * self.block_frame // zc
+        self.crossfade_frame = int(np.round(crossfade_time * samplerate / zc)) * zc
+        self.sola_buffer_frame = min(self.crossfade_frame, 4 * zc)
+        self.sola_search_frame = zc
+        self.extra_frame = int(np.round(extra_time * samplerate / zc)) * zc
+        self.input_wav = torch.zeros(self.extra_frame + self.crossfade_frame + self.sola_search_frame + self.block_frame)
+        self.input_wav_denoise = self.input_wav.clone()
+        self.input_wav_res = torch.zeros(160 * self.input_wav.shape[0] // zc)
+        self.rms_buffer = np.zeros(4 * zc, dtype="float32")
+        self.nr_buffer = torch.zeros(self.sola_buffer_frame)
+        self.output_buffer = self.input_wav.clone()
+        self.skip_head = self.extra_frame // zc
+        self.return_length = (self.block_frame + self.sola_buffer_frame + self.sola_search_frame) // zc
+        self.fade_in_window, self.fade_out_window = fade_windows(self.sola_buffer_frame)
+        self.resampler = tat.Resample(orig_freq=samplerate, new_freq=16000, dtype=torch.float32)
+        self.resampler2 = tat.Resample(orig_freq=rvc.tgt_sr, new_freq=samplerate, dtype=torch.float32) if rvc.tgt_sr != samplerate else None
+        self.tg = lambda x, xn: OT.torchgate(x, xn, samplerate, 4 * zc, prop_decrease=0.9)           # gui.py:869-871
+        self.tail = SolaTail(self.block_frame, self.sola_buffer_frame, self.sola_search_frame)
+        self.last = {}
+
+    @torch.no_grad()
+    def block(self, indata: np.ndarray) -> np.ndarray:
+        zc = self.zc
+        indata = np.asarray(indata, dtype=np.float32).copy()
+        if self.threhold > -60:                                                                        # gui.py:951-966
+            indata = np.append(self.rms_buffer, indata)
+            rms = rms_frames(indata, 4 * zc, zc)[:, 2:]
+            self.rms_buffer[:] = indata[-4 * zc:]
+            indata = indata[2 * zc - zc // 2:]
+            db = 20.0 * np.log10(np.maximum(1e-5, rms))                                                # librosa.amplitude_to_db(ref=1.0):
+            db = np.maximum(db, db.max() - 80.0)                                                       # amin 1e-5, top_db 80
+            db_threhold = db[0] < self.threhold
+            for i in range(db_threhold.shape[0]):
+                if db_threhold[i]:
+                    indata[i * zc: (i + 1) * zc] = 0
+            indata = indata[zc // 2:]
+        self.input_wav[: -self.block_frame] = self.input_wav[self.block_frame:].clone()
+        self.input_wav[-indata.shape[0]:] = torch.from_numpy(indata)
+        self.input_wav_res[: -self.block_frame_16k] = self.input_wav_res[self.block_frame_16k:].clone()
+        if self.I_noise_reduce:                                                                        # gui.py:974-993
+            self.input_wav_denoise[: -self.block_frame] = self.input_wav_denoise[self.block_frame:].clone()
+            input_wav = self.input_wav[-self.sola_buffer_frame - self.block_frame:]
+            input_wav = self.tg(input_wav.unsqueeze(0), self.input_wav.unsqueeze(0)).squeeze(0)
+            input_wav[: self.sola_buffer_frame] *= self.fade_in_window
+            input_wav[: self.sola_buffer_frame] += self.nr_buffer * self.fade_out_window
+            self.input_wav_denoise[-self.block_frame:] = input_wav[: self.block_frame]
+            self.nr_buffer[:] = input_wav[self.block_frame:]
+            self.input_wav_res[-self.block_frame_16k - 160:] = self.resampler(self.input_wav_denoise[-self.block_frame - 2 * zc:])[160:]
+        else:
+            self.input_wav_res[-160 * (indata.shape[0] // zc + 1):] = self.resampler(self.input_wav[-indata.shape[0] - 2 * zc:])[160:]
+        infer_wav = torch.from_numpy(self.rvc.infer(self.input_wav_res.numpy(), self.block_frame_16k, self.skip_head, self.return_length))
+        if self.resampler2 is not None:
+            infer_wav = self.resampler2(infer_wav)
+        if self.O_noise_reduce:                                                                        # gui.py:1015-1023
+            self.output_buffer[: -self.block_frame] = self.output_buffer[self.block_frame:].clone()
+            self.output_buffer[-self.block_frame:] = infer_wav[-self.block_frame:]
+            infer_wav = self.tg(infer_wav.unsqueeze(0), self.output_buffer.unsqueeze(0)).squeeze(0)
+        if self.rms_mix_rate < 1:
+            src = self.input_wav_denoise if self.I_noise_reduce else self.input_wav
+            infer_wav = envelope_mix(infer_wav, src[self.extra_frame:], zc, self.rms_mix_rate)
+        self.last = {"infer_wav": infer_wav.clone(), "input_wav_res": self.input_wav_res.clone()}
+        out, off = self.tail.step(infer_wav)
+        self.last["offset"] = off
+        return out.numpy()

@@ -22,7 +22,7 @@ using namespace rvcb;
 
 namespace {
 
-constexpr int N_FFT = 1024, HOP = 160, N_MELS = 128, N_BINS = 513, N_CLASS = 360;
+constexpr int N_FFT = 1024, HOP = 160, N_MELS = 128, N_BINS = 513, N_CLASS = 360, DFT_NPAD = 1088;
 
 struct ConvBN {              // conv3x3 (BN folded)
     PackedB w; float* b; int cin, cout, bk;
@@ -57,6 +57,7 @@ struct rvcb_rmvpe {
     DevOwner own;
     Arena arena;
     float* dft = nullptr;         // [1026, 1024] windowed cos | -sin
+    __half* dft16 = nullptr;      // [1088, 3072] the same basis as fp16 (hi | lo | hi / 2048): split-precision tensor-core DFT
     float* melw = nullptr;        // [128, 513]
     // stem (encoder level 0 block 0, C_in = 1): bn0 scalar affine, conv1 1->16 (BN folded), shortcut 1->16
     float bn0_s = 1.f, bn0_b = 0.f;
@@ -101,6 +102,19 @@ static rvcb_rmvpe* rmvpe_build(const rvcb_weights& w) {
                     d[(size_t)(N_BINS + k) * N_FFT + n] = (float)(-win * std::sin(ph));
                 }
             h->dft = own.upload(d);
+            // b = hi + lo with hi = fp16(b), lo = fp16(b - hi): 22 significant bits; the third copy (hi / 2048, exact unless
+            // subnormal) pairs with the x2048-scaled low half of the signal (rmvpe_split_kernel)
+            std::vector<__half> d16((size_t)DFT_NPAD * 3 * N_FFT, __float2half(0.f));
+            for (int r = 0; r < 2 * N_BINS; ++r)
+                for (int n = 0; n < N_FFT; ++n) {
+                    const float b = d[(size_t)r * N_FFT + n];
+                    const __half hi = __float2half_rn(b);
+                    const float hf = __half2float(hi);
+                    d16[(size_t)r * 3 * N_FFT + n] = hi;
+                    d16[(size_t)r * 3 * N_FFT + N_FFT + n] = __float2half_rn(b - hf);
+                    d16[(size_t)r * 3 * N_FFT + 2 * N_FFT + n] = __float2half_rn(hf * (1.f / 2048.f));
+                }
+            h->dft16 = own.upload(d16);
             // librosa.filters.mel(sr=16000, n_fft=1024, n_mels=128, fmin=30, fmax=8000, htk=True), slaney norm (mel.py:27-34)
             std::vector<double> melf(N_MELS + 2);
             const double lo = 2595.0 * std::log10(1.0 + 30.0 / 700.0), hi = 2595.0 * std::log10(1.0 + 8000.0 / 700.0);
@@ -209,6 +223,23 @@ __global__ void reflect_pad_kernel(const float* __restrict__ x, int n, float* __
     if (j < 0) j = -j;
     if (j >= n) j = 2L * (n - 1) - j;
     y[i] = x[j];
+}
+
+// Reflect-padded signal as two fp16 planes of one [2R, HOP] matrix: rows [0, R) hold hi = fp16(x), rows [R, 2R) hold
+// fp16((x - hi) * 2048); elements past n + 2 * pad are zero.
+__global__ void rmvpe_split_kernel(const float* __restrict__ x, int n, int pad, int R, __half* __restrict__ y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)R * HOP) return;
+    float v = 0.f;
+    if (i < (long)n + 2 * pad) {
+        long j = i - pad;
+        if (j < 0) j = -j;
+        if (j >= n) j = 2L * (n - 1) - j;
+        v = x[j];
+    }
+    const __half hi = __float2half_rn(v);
+    y[i] = hi;
+    y[(long)R * HOP + i] = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
 
 __global__ void magnitude_kernel(const float* __restrict__ spec, float* __restrict__ mag, int nf) {
@@ -572,7 +603,7 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     const int T = round_up(nf, 32);
     auto rnd = [](size_t b) { return (b + 1023) & ~size_t(1023); };
     size_t need = 64u << 20;
-    need += rnd(((size_t)n + N_FFT) * 4) + rnd((size_t)nf * 2 * N_BINS * 4) + rnd((size_t)nf * N_BINS * 4) + 2 * rnd((size_t)T * 128 * 4);
+    need += 2 * rnd(((size_t)n + N_FFT + 4 * HOP) * 4) + rnd((size_t)nf * 2 * N_BINS * 4) + rnd((size_t)nf * N_BINS * 4) + 2 * rnd((size_t)T * 128 * 4);
     const size_t px = (size_t)T * 128;
     need += 3 * rnd(px * 16 * 4) + 3 * rnd(px * 16 * 2);        // ping-pong fp32, sc32, fp16 x2, t16 (level-0 size bounds all levels)
     for (int l = 0; l < 5; ++l) need += rnd((px >> (2 * l)) * (32u << l) * 2);   // concat buffers
@@ -582,11 +613,32 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     Arena& ar = h->arena;
 
     // ---- log-mel ----
-    float* wpad = ar.alloc<float>((size_t)n + N_FFT);
-    reflect_pad_kernel<<<(unsigned)ceil_div_l((long)n + N_FFT, 256), 256, 0, st>>>(d_wav, n, wpad, N_FFT / 2);
-    KERNEL_CHECK();
     float* spec = ar.alloc<float>((size_t)nf * 2 * N_BINS);
-    sgemm_nt(wpad, HOP, h->dft, N_FFT, spec, 2 * N_BINS, nf, 2 * N_BINS, N_FFT, st);       // overlapping frames: lda = hop
+    static const bool mel_fp32 = [] { const char* e = getenv("RVCB_MEL_FP32"); return e && e[0] == '1'; }();
+    if (mel_fp32) {
+        float* wpad = ar.alloc<float>((size_t)n + N_FFT);
+        reflect_pad_kernel<<<(unsigned)ceil_div_l((long)n + N_FFT, 256), 256, 0, st>>>(d_wav, n, wpad, N_FFT / 2);
+        KERNEL_CHECK();
+        sgemm_nt(wpad, HOP, h->dft, N_FFT, spec, 2 * N_BINS, nf, 2 * N_BINS, N_FFT, st);       // overlapping frames: lda = hop
+    } else {
+        // Split-precision DFT on the tensor cores: x = hi + lo / 2048 and b = hi + lo in fp16, the three significant products
+        // (hi.hi, hi.lo, lo.hi) accumulate in fp32 (the dropped lo.lo term is 2^-22 relative).  A frame is the signal viewed as
+        // rows of HOP samples: frame t = rows t .. t+6 (6 x 160 + 64 = 1024), i.e. a 7-tap "convolution" over hop-sized rows,
+        // so the operand needs no overlapping-row tensor map and no im2col.
+        const int R = (int)ceil_div_l((long)n + N_FFT, HOP) + 1;
+        __half* ws = ar.alloc<__half>((size_t)2 * R * HOP + 64);
+        rmvpe_split_kernel<<<(unsigned)ceil_div_l((long)R * HOP, 256), 256, 0, st>>>(d_wav, n, N_FFT / 2, R, ws);
+        KERNEL_CHECK();
+        GemmArgs g;
+        g.A = ws; g.lda = HOP; g.a_rows = 2 * R; g.a_cols = HOP;
+        g.B = h->dft16; g.ldb = 3 * N_FFT; g.b_rows = 2 * N_BINS; g.b_cols = 3 * N_FFT;
+        g.M = nf; g.N = 2 * N_BINS; g.block_k = 32;
+        g.nseg = 0;
+        for (int part = 0; part < 3; ++part)
+            for (int j = 0; j < 7; ++j) g.seg[g.nseg++] = {(part == 2 ? R : 0) + j, 0, 0, j < 6 ? HOP / 32 : (N_FFT - 6 * HOP) / 32};
+        g.out32 = spec; g.ld32 = 2 * N_BINS;
+        gemm(g, st);
+    }
     float* mag = ar.alloc<float>((size_t)nf * N_BINS);
     magnitude_kernel<<<(unsigned)ceil_div_l((long)nf * N_BINS, 256), 256, 0, st>>>(spec, mag, nf);
     KERNEL_CHECK();

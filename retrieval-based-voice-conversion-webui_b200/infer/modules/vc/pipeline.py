@@ -70,6 +70,9 @@ class Pipeline(object):
         self.f0_gen = Generator(rmvpe_root, self.is_half, self.x_pad, self.device, self.window, self.sr)
         self._index_cache = {}
         self._side = torch.cuda.Stream(device=self.device)
+        # RMVPE ends in the serial BiGRU and is the longer front branch: it gets a high-priority stream so that its CTAs are placed
+        # first whenever SMs free up, and HuBERT + retrieval fill the rest (RVCB_F0_PRIO=0: RMVPE stays on the caller's stream)
+        self._f0_stream = torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("RVCB_F0_PRIO", "1") != "0" else None
         self._prefetched = None
         self._pinned = None          # reusable pinned staging buffer for the H2D copy of the utterance
         self._graphs = {}            # (length, settings) -> captured CUDA graph of the device-resident utterance path
@@ -208,13 +211,28 @@ class Pipeline(object):
             cur = torch.cuda.current_stream()
             fork = torch.cuda.Event()
             fork.record(cur)                       # the side stream depends on the padded audio only, not on RMVPE
-            # the two branches are independent: cap their persistent grids at half the SMs each, so that kernels of the two
-            # streams run side by side instead of taking turns at the whole chip (measured: profiles/README.md, r2)
-            cap_prev = engine.set_grid_cap(engine.front_branch_cap())
+            # the two branches are independent.  HuBERT + retrieval launch with their persistent grids capped at half the SMs
+            # (RVCB_FRONT_CAP), RMVPE -- the longer branch, on the high-priority stream -- uncapped (RVCB_F0_CAP, 0 = no cap), so
+            # that kernels of the two streams run side by side instead of taking turns at the whole chip.  Measured (whole step,
+            # profiles/README.md r2k): both capped, no priority 7.56 ms; priority + RMVPE uncapped 7.43 ms; nothing capped 7.73 ms
+            cap_prev = engine.set_grid_cap(int(os.environ.get("RVCB_F0_CAP", "0")))
             try:
                 # f0 first: RMVPE has the fewer launches, so both branches are in flight sooner when launching eagerly
-                pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
+                if self._f0_stream is not None:
+                    self._f0_stream.wait_event(fork)
+                    with torch.cuda.stream(self._f0_stream):
+                        pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
+                        f0_done = torch.cuda.Event()
+                        f0_done.record(self._f0_stream)
+                    cur.wait_event(f0_done)
+                    if not capturing:
+                        audio_pad.record_stream(self._f0_stream)
+                        pitch.record_stream(cur)
+                        pitchf.record_stream(cur)
+                else:
+                    pitch, pitchf = self.f0_gen.calculate_device(audio_pad, p_len, f0_up_key)
                 pitch, pitchf = pitch.unsqueeze(0), pitchf.unsqueeze(0)
+                engine.set_grid_cap(engine.front_branch_cap())
                 self._side.wait_event(fork)
                 with torch.cuda.stream(self._side):
                     f, f_raw = self._features(model, audio_pad, index, big_npy, index_rate, version)

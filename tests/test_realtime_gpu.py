@@ -93,3 +93,56 @@ def test_realtime_tail_matches_oracle(rate):
         assert (got - ref).abs().max().item() < 2e-5, (b, (got - ref).abs().max().item())
         assert (tail.sola_buffer.cpu() - ot.sola_buffer).abs().max().item() < 2e-5
     assert len(set(offs[1:])) > 1
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(samplerate=48000, I_noise_reduce=True, O_noise_reduce=True, rms_mix_rate=0.5, threhold=-60.0),
+    dict(samplerate=40000, I_noise_reduce=False, O_noise_reduce=False, rms_mix_rate=1.0, threhold=-45.0),
+])
+def test_realtime_block_matches_oracle_callback(cfg):
+    """The whole device side of gui.py's audio callback (gui.py:940-1090) as ONE object / one CUDA graph per block -- input ring,
+    TorchGate on input and output, resamplers (incl. model rate != device rate), RVC.infer with its own RMVPE, envelope mix, SOLA --
+    against the oracle restatement (OracleCallback) over consecutive blocks: eager, capture, replays.  Noise draws are shared
+    through device buffers the captured graph reads in place."""
+    from oracle import ivf as OI, rtrvc as ORT, weights as OW
+    from infer.lib.rtrvc import RVC
+    from infer.modules.gui import RealtimeBlock
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    sr = cfg["samplerate"]
+    hw, rw, sw = OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234)
+    idx = OI.build_ivf(OW.index_vectors(2000, 768, 1).numpy(), None, seed=0, exact_assign=True)
+    orc_rvc = ORT.OracleRVC(hw, rw, sw, OW.V2_48K_CONFIG, idx, 0.5, key=0, noise_seed=11)
+    orc = ORT.OracleCallback(orc_rvc, samplerate=sr, block_time=0.16, crossfade_time=0.05, extra_time=2.5, I_noise_reduce=cfg["I_noise_reduce"],
+                             O_noise_reduce=cfg["O_noise_reduce"], rms_mix_rate=cfg["rms_mix_rate"], threhold=cfg["threhold"])
+    rt = RVC(0, 0, OW.synth_cpt(1234, "v2"), Index.from_oracle_layout(idx), 0.5, device="cuda:0", hubert_model=HubertB200(hw, "cuda:0"),
+             rmvpe_state_dict=rw)
+    blk = RealtimeBlock(rt, samplerate=sr, block_time=0.16, crossfade_time=0.05, extra_time=2.5, I_noise_reduce=cfg["I_noise_reduce"],
+                        O_noise_reduce=cfg["O_noise_reduce"], rms_mix_rate=cfg["rms_mix_rate"], threhold=cfg["threhold"], device="cuda:0")
+    assert (blk.block_frame, blk.skip_head, blk.return_length) == (orc.block_frame, orc.skip_head, orc.return_length)
+    n_blocks = 5
+    mic = OW.synth_voice(0.16 * n_blocks + 0.1, sr=sr, seed=31).numpy()
+    mic[: orc.block_frame // 2] *= 0.001                      # a quiet stretch for the threshold gate to act on
+    nb, agree, errs = None, 0, []
+    for b in range(n_blocks):
+        ind = mic[b * orc.block_frame: (b + 1) * orc.block_frame]
+        ref = orc.block(ind)
+        tap = orc_rvc.taps[-1]
+        if nb is None:
+            nb = (torch.empty_like(tap["noise"][0], device="cuda"), torch.empty_like(tap["noise"][1], device="cuda"))
+        nb[0].copy_(tap["noise"][0]); nb[1].copy_(tap["noise"][1])
+        rt.net_g._noise[:] = [nb]
+        got = blk.process(ind)
+        rt.net_g._noise.clear()
+        assert got.shape == ref.shape == (orc.block_frame,)
+        res_err = (blk.input_wav_res.cpu() - orc.last["input_wav_res"]).abs().max().item()
+        off = int(blk.tail.last_offset.item()) if blk.tail.last_offset is not None else None
+        rms = float(np.sqrt(np.mean((got - ref) ** 2)) / max(np.sqrt(np.mean(ref ** 2)), 1e-6))
+        print(f"[parity] callback block {b} sr={sr}: 16 kHz window max err {res_err:.2e}, SOLA offset {off} vs {orc.last['offset']}, "
+              f"block rel RMS err {rms:.3e} ({'graph' if any('graph' in e for e in blk._graphs.values()) else 'eager'})")
+        assert res_err < 2e-4
+        if off is None or off == orc.last["offset"]:
+            agree += 1
+            errs.append(rms)
+    assert any("graph" in e for e in blk._graphs.values())
+    assert agree >= n_blocks - 1 and max(errs) < 1e-2, (agree, errs)

@@ -64,48 +64,49 @@ def graph_time(name, fn, reps=20):
     return out
 
 
-a16 = graph_time("prologue: sosfiltfilt", lambda: engine.sosfiltfilt(P.sos_h, P.sos_zi_h, 3 * max(len(P.ah), len(P.bh)), x_dev))
-audio_pad = graph_time("prologue: reflect_pad", lambda: engine.reflect_pad(a16, pipe.t_pad))
-p_len = audio_pad.numel() // pipe.window
-pp = graph_time("RMVPE + f0 post (alone, all SMs)", lambda: pipe.f0_gen.calculate_device(audio_pad, p_len, 0))
-ff = graph_time("HuBERT + retrieval + blend (alone, all SMs)", lambda: pipe._features(vc.hubert_model, audio_pad, index, index.vectors, 0.75, "v2"))
-graph_time("HuBERT only", lambda: vc.hubert_model.extract_features(source=audio_pad.view(1, -1), padding_mask=None, output_layer=12))
+if not os.environ.get("ONLY_STEP"):
+    a16 = graph_time("prologue: sosfiltfilt", lambda: engine.sosfiltfilt(P.sos_h, P.sos_zi_h, 3 * max(len(P.ah), len(P.bh)), x_dev))
+    audio_pad = graph_time("prologue: reflect_pad", lambda: engine.reflect_pad(a16, pipe.t_pad))
+    p_len = audio_pad.numel() // pipe.window
+    pp = graph_time("RMVPE + f0 post (alone, all SMs)", lambda: pipe.f0_gen.calculate_device(audio_pad, p_len, 0))
+    ff = graph_time("HuBERT + retrieval + blend (alone, all SMs)", lambda: pipe._features(vc.hubert_model, audio_pad, index, index.vectors, 0.75, "v2"))
+    graph_time("HuBERT only", lambda: vc.hubert_model.extract_features(source=audio_pad.view(1, -1), padding_mask=None, output_layer=12))
 
 
-def both():
-    cur = torch.cuda.current_stream()
-    fork = torch.cuda.Event()
-    fork.record(cur)
-    prev = engine.set_grid_cap(engine.front_branch_cap())
+    def both():
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        prev = engine.set_grid_cap(engine.front_branch_cap())
+        try:
+            r = pipe.f0_gen.calculate_device(audio_pad, p_len, 0)
+            pipe._side.wait_event(fork)
+            with torch.cuda.stream(pipe._side):
+                f = pipe._features(vc.hubert_model, audio_pad, index, index.vectors, 0.75, "v2")
+                ev = torch.cuda.Event()
+                ev.record(pipe._side)
+        finally:
+            engine.set_grid_cap(prev)
+        cur.wait_event(ev)
+        return r, f
+
+
+    graph_time("both front branches (fork / join, grid cap)", both)
+    pitch, pitchf = pp[0].unsqueeze(0), pp[1].unsqueeze(0)
+
+
+    def synth(trim):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        pipe._prefetched = (audio_pad, ff[0], ff[1], ev)
+        return pipe._vc_dev(vc.hubert_model, vc.net_g, sid, audio_pad, pitch, pitchf, [0, 0, 0], index, index.vectors, 0.75, "v2", 0.33, trim=trim)
+
+
     try:
-        r = pipe.f0_gen.calculate_device(audio_pad, p_len, 0)
-        pipe._side.wait_event(fork)
-        with torch.cuda.stream(pipe._side):
-            f = pipe._features(vc.hubert_model, audio_pad, index, index.vectors, 0.75, "v2")
-            ev = torch.cuda.Event()
-            ev.record(pipe._side)
-    finally:
-        engine.set_grid_cap(prev)
-    cur.wait_event(ev)
-    return r, f
-
-
-graph_time("both front branches (fork / join, grid cap)", both)
-pitch, pitchf = pp[0].unsqueeze(0), pp[1].unsqueeze(0)
-
-
-def synth(trim):
-    ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream())
-    pipe._prefetched = (audio_pad, ff[0], ff[1], ev)
-    return pipe._vc_dev(vc.hubert_model, vc.net_g, sid, audio_pad, pitch, pitchf, [0, 0, 0], index, index.vectors, 0.75, "v2", 0.33, trim=trim)
-
-
-try:
-    out = graph_time("upsample/protect + synthesizer (keep mode)", lambda: synth(True))
-    graph_time("upsample/protect + synthesizer (full decode)", lambda: synth(False))
-    graph_time("epilogue: rms mix + scale + int16", lambda: engine.f32_to_i16(engine.post_mix(out.contiguous(), 48000, a16, 0.25)))
-except Exception as e:                                   # _prefetched contract differs: report and go on
-    print("synth stage skipped:", repr(e)[:300])
+        out = graph_time("upsample/protect + synthesizer (keep mode)", lambda: synth(True))
+        graph_time("upsample/protect + synthesizer (full decode)", lambda: synth(False))
+        graph_time("epilogue: rms mix + scale + int16", lambda: engine.f32_to_i16(engine.post_mix(out.contiguous(), 48000, a16, 0.25)))
+    except Exception as e:                                   # _prefetched contract differs: report and go on
+        print("synth stage skipped:", repr(e)[:300])
 graph_time("whole step (product _dev_body)", lambda: pipe._dev_body(x_dev, vc.hubert_model, vc.net_g, sid, [0, 0, 0], 0, index, index.vectors,
                                                                     0.75, 1, 48000, 0.25, "v2", 0.33, True))
