@@ -39,6 +39,8 @@ class VC:
         self.net_g = None
         self.cpt: Optional[dict] = None
         self.n_spk = self.tgt_sr = self.version = self.if_f0 = None
+        self._loaded_sid = None
+        self._lanes: List["VC"] = []          # extra conversion lanes of vc_multi (own handles / streams / graphs each)
 
     # ------------------------------------------------------------------ model selection (modules.py:32-117)
     def _protect_updates(self, extra: tuple) -> Tuple[Dict[str, Any], Dict[str, Any]]:
@@ -52,10 +54,13 @@ class VC:
             return
         logger.info("Clean model cache")
         self.hubert_model = self.net_g = self.n_spk = self.tgt_sr = None
+        self._lanes.clear()
         torch.cuda.empty_cache()
 
     def _load(self, sid) -> str:
         """Build the synthesizer container and the pipeline for ``sid`` (a file under $weight_root, or the dict a .pth holds)."""
+        self._loaded_sid = sid
+        self._lanes.clear()
         if isinstance(sid, dict):
             self.net_g, self.cpt = get_synthesizer(sid, self.config.device)
             name = sid.get("name", "in-memory")
@@ -148,18 +153,47 @@ class VC:
             traceback.print_exc()
         return [p.name for p in uploads]
 
+    def _lane(self, i: int) -> "VC":
+        """Lane 0 is this object; lane i > 0 is a private copy of the loaded models (own synthesizer container, HuBERT handle,
+        Pipeline with its RMVPE, streams and captured graphs): the library's workspaces are per handle, so utterances that are in
+        flight at the same time must not share handles."""
+        if i == 0:
+            return self
+        while len(self._lanes) < i:
+            lane = VC(self.config)
+            lane._load(self._loaded_sid)
+            if self.hubert_model is None:
+                self.hubert_model = load_hubert(self.config.device, self.config.is_half)
+            lane.hubert_model = self.hubert_model.clone() if hasattr(self.hubert_model, "clone") else load_hubert(self.config.device,
+                                                                                                               self.config.is_half)
+            self._lanes.append(lane)
+        return self._lanes[i - 1]
+
     def vc_multi(self, sid, dir_path, opt_root, paths, f0_up_key, f0_method, file_index, file_index2, index_rate, filter_radius,
                  resample_sr, rms_mix_rate, protect, format1) -> Iterator[str]:
+        """modules.py:201-266.  The reference converts the files one after the other; one utterance is latency-bound on a B200 (two
+        front branches of ~130 small launches each, then the synthesizer), so RVCB_LANES (default 2) utterances are kept in flight
+        on one GPU, each on its own lane (thread + streams + handles); results are identical to the serial loop and the log lines
+        come out in the input order.  Under torchrun the list is additionally strided over ranks (one process per GPU)."""
         try:
             dir_path, opt_root = _unquote(dir_path), _unquote(opt_root)
             os.makedirs(opt_root, exist_ok=True)
             todo = self._inputs(dir_path, paths)
-            # the reference is a serial loop on one device; under torchrun the list is strided over ranks exactly like
-            # extract_feature_print.py:110
+            # under torchrun the list is strided over ranks exactly like extract_feature_print.py:110
             rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-            log: List[str] = []
-            for path in todo[rank::world]:
-                info, opt = self.vc_single(sid, path, f0_up_key, None, f0_method, file_index, file_index2, index_rate, filter_radius,
+            todo = todo[rank::world]
+            n_lanes = max(1, min(int(os.environ.get("RVCB_LANES", "2")), len(todo)))
+
+            index_clones: Dict[int, Any] = {}
+
+            def convert(lane_id: int, path: str) -> str:
+                lane = self._lane(lane_id)
+                fi = file_index
+                if lane_id > 0 and hasattr(file_index, "clone") and not isinstance(file_index, str):
+                    if lane_id not in index_clones:                  # a device-resident Index object: one handle per lane
+                        index_clones[lane_id] = file_index.clone()
+                    fi = index_clones[lane_id]
+                info, opt = lane.vc_single(sid, path, f0_up_key, None, f0_method, fi, file_index2, index_rate, filter_radius,
                                            resample_sr, rms_mix_rate, protect)
                 if "Success" in info:
                     try:
@@ -167,8 +201,39 @@ class VC:
                         save_audio("%s/%s.%s" % (opt_root, os.path.basename(path), format1), wav, out_sr, f32=True)
                     except Exception:
                         info += traceback.format_exc()
-                log.append("%s->%s" % (os.path.basename(path), info))
+                return "%s->%s" % (os.path.basename(path), info)
+
+            log: List[str] = []
+            if n_lanes == 1 or self.net_g is None:
+                for path in todo:
+                    log.append(convert(0, path))
+                    yield "\n".join(log)
+            else:
+                import queue
+                from concurrent.futures import ThreadPoolExecutor
+                # the first file goes through lane 0 alone: one-time kernel attribute setup and arena sizing happen single-threaded
+                log.append(convert(0, todo[0]))
                 yield "\n".join(log)
+                for i in range(1, n_lanes):
+                    self._lane(i)
+                free: "queue.Queue[int]" = queue.Queue()
+                for i in range(n_lanes):
+                    free.put(i)
+                device = torch.device(self.config.device if "cuda" in str(self.config.device) else "cuda:0")
+                streams = [torch.cuda.Stream(device=device) for _ in range(n_lanes)]
+
+                def work(path: str) -> str:
+                    lane_id = free.get()
+                    try:
+                        with torch.cuda.device(device), torch.cuda.stream(streams[lane_id]):
+                            return convert(lane_id, path)
+                    finally:
+                        free.put(lane_id)
+
+                with ThreadPoolExecutor(max_workers=n_lanes, thread_name_prefix="vc_lane") as pool:
+                    for line in pool.map(work, todo[1:]):       # results in input order
+                        log.append(line)
+                        yield "\n".join(log)
             yield "\n".join(log)
         except Exception:
             yield traceback.format_exc()

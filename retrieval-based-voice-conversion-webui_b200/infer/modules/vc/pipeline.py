@@ -270,7 +270,7 @@ class Pipeline(object):
                 ent["x"] = torch.empty_like(x)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):       # other vc_multi lanes keep running
                     ent["out"] = self._dev_body(ent["x"], *args)
                 ent["graph"] = g
             except Exception:                           # capture is an optimisation only: keep launching eagerly for this key

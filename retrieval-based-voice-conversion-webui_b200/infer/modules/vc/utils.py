@@ -62,6 +62,7 @@ class HubertB200:
 
     def __init__(self, state_dict: dict, device="cuda:0"):
         self.device = torch.device(device if "cuda" in str(device) else "cuda:0")
+        self._state = state_dict                       # kept for clone(): a second lane needs its own handle (arenas are per handle)
         self._m = Hubert({k: v.float() for k, v in state_dict.items() if torch.is_tensor(v) and v.is_floating_point()},
                          self.device.index or 0)
 
@@ -69,6 +70,10 @@ class HubertB200:
     def float(self): return self
     def eval(self): return self
     def to(self, *a, **k): return self
+
+    def clone(self) -> "HubertB200":
+        """A second handle over the same weights (own workspace): one per concurrent lane of ``VC.vc_multi``."""
+        return HubertB200(self._state, self.device)
 
     @torch.no_grad()
     def extract_features(self, source, padding_mask=None, mask=False, output_layer=None):

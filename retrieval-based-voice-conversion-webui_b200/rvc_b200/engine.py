@@ -115,6 +115,7 @@ class Index:
         li = np.ascontiguousarray(list_ids, dtype=np.int64)
         self.ntotal, self.d = self.vectors.shape
         self.nlist = self.centroids.shape[0]
+        self._lists = (lo, li)
         self.device = torch.device("cuda", device)
         self.h = C.c_void_p()
         _lib.check(_lib.lib().rvcb_index_create(self.centroids.ctypes.data_as(C.c_void_p), self.nlist,
@@ -126,6 +127,11 @@ class Index:
         """idx: any object with .centroids, .vectors, .list_off, .list_ids (e.g. oracle.ivf.IVFFlat or the
         .index reader)."""
         return cls(idx.centroids, idx.vectors, idx.list_off, idx.list_ids, device)
+
+    def clone(self) -> "Index":
+        """A second device handle over the same host arrays (the search workspace is per handle: utterances in flight at the same
+        time -- VC.vc_multi lanes -- must not share one)."""
+        return Index(self.centroids, self.vectors, self._lists[0], self._lists[1], self.device.index or 0)
 
     def reconstruct_n(self, i0: int, n: int) -> np.ndarray:
         return self.vectors[i0:i0 + n]

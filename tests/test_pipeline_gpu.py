@@ -177,6 +177,52 @@ def test_vc_single_with_index_file_and_vc_multi(tmp_path):
     assert sr == 48000 and len(y) > 40000
 
 
+def test_vc_multi_lanes_equal_the_serial_loop(tmp_path, monkeypatch):
+    """SURVEY 8f-3 (batched front door) as built: ``vc_multi`` keeps RVCB_LANES utterances in flight on one GPU, each on its own
+    lane (thread, streams, handles, captured graph).  With the noise draws pinned, the files written by two lanes equal the files
+    of the serial loop sample for sample, and the log lines keep the input order."""
+    from scipy.io import wavfile
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup(1.0, 800)
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    vc = VC(cfg)
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    vc.get_vc(OW.synth_cpt(1234, "v2"))
+    gidx = Index.from_oracle_layout(idx)
+    indir = tmp_path / "in"
+    indir.mkdir()
+    names = [f"u{i}.wav" for i in range(6)]
+    for i, nm in enumerate(names):
+        wavfile.write(str(indir / nm), 16000, (OW.synth_voice(1.0, seed=40 + i).numpy() * 32767).astype(np.int16))
+    monkeypatch.setattr(VC, "_inputs", staticmethod(lambda d, u: [os.path.join(d, n) for n in names]))     # listdir order is arbitrary
+    n_pad = 16000 + 2 * 16000 * cfg.x_pad
+    T = min(2 * ((n_pad - 400) // 320 + 1), n_pad // 160)          # synthesizer frames: min(2 x HuBERT frames, p_len), pipeline.py:142-146
+    g = torch.Generator().manual_seed(3)
+    n1 = torch.randn(1, 192, T, generator=g).cuda()
+    n2 = torch.randn(1, T * 480, 1, generator=g).cuda()
+    results = {}
+    for lanes in (1, 2):
+        monkeypatch.setenv("RVCB_LANES", str(lanes))
+        outdir = tmp_path / f"out{lanes}"
+        containers = [vc.net_g] + ([vc._lane(1).net_g] if lanes > 1 else [])
+        for c in containers:
+            c._noise.clear()
+            for _ in range(len(names)):
+                c.set_noise(n1, n2)
+        msgs = list(vc.vc_multi(0, str(indir), str(outdir), [], 0, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33, "wav"))
+        lines = msgs[-1].split("\n")
+        assert [ln.split("->")[0] for ln in lines] == names and all("Success" in ln for ln in lines), msgs[-1]
+        results[lanes] = [wavfile.read(str(outdir / (nm + ".wav")))[1] for nm in names]
+    for c in [vc.net_g, vc._lane(1).net_g]:
+        c._noise.clear()
+    for a, b in zip(results[1], results[2]):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert not np.array_equal(results[1][0], results[1][1])
+
+
 def test_no_f0_model_through_the_facade_and_realtime_engine():
     """cpt["f0"] == 0 end to end: get_vc picks the no-f0 container (modules.py:87-99 class table), the pipeline skips
     RMVPE (pipeline.py:203) and passes pitch=None, rtrvc skips its pitch cache (rtrvc.py:if_f0)."""
