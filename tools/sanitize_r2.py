@@ -1,5 +1,7 @@
 """Small invocations of the round-2 kernels for compute-sanitizer (memcheck / racecheck / synccheck): the fused residual block
-(streamed and resident weights), the fused attention (through HuBERT), the tensor-core kNN short list, the realtime tail."""
+(streamed and resident weights), the fused attention (through HuBERT), the tensor-core kNN short list, the realtime tail, and
+(SANITIZE_MORE=1) the halo convolutions + split-precision DFT through a short RMVPE run, the spectral gate, the resampler and the
+keep-mode synthesizer."""
 import ctypes as C
 import os
 import sys
@@ -33,5 +35,21 @@ D1, I1 = engine.FlatIndex(db).search(q)
 assert torch.equal(I0, I1) and torch.equal(D0, D1)
 buf = torch.zeros(1920, device="cuda")
 out = engine.rt_tail(torch.randn(10080, generator=g).cuda(), torch.randn(10600, generator=g).cuda(), 480, 0.0, buf, 7680, 480)
+if os.environ.get("SANITIZE_MORE"):
+    rm = engine.Rmvpe(SY.rmvpe_weights(4321))
+    f0 = rm.infer(SY.synth_voice(0.35, seed=3).cuda(), 0.03)[0]              # conv2d_row / conv2d_tile / split DFT / GRU
+    from infer.modules.gui import Resample, TorchGate
+    xn = torch.randn(1, 9600, generator=g).cuda() * 0.1
+    yg = TorchGate(sr=48000, n_fft=1920, prop_decrease=0.9).to("cuda:0")(xn[:, -3840:].contiguous(), xn)
+    yr = Resample(48000, 16000).to("cuda:0")(xn[0])
+    cfg = SY.V2_48K_CONFIG if hasattr(SY, "V2_48K_CONFIG") else None
+    if cfg is not None:
+        syn = engine.Synth(SY.synth_weights(1234), cfg, 768)
+        T = 150
+        kept = syn.infer_keep((torch.randn(T, 768, generator=g) * 0.5).cuda(), 0, torch.randint(1, 255, (T,), generator=g).cuda(),
+                              (torch.rand(T, generator=g) * 300 + 80).cuda(), torch.randn(192, T, generator=g).cuda(),
+                              torch.randn(T * 480, generator=g).cuda(), 40, 60)
+        assert torch.isfinite(kept).all()
+    assert torch.isfinite(f0).all() and torch.isfinite(yg).all() and torch.isfinite(yr).all()
 torch.cuda.synchronize()
 print("ok", feats.shape, float(out.abs().max()))
