@@ -431,6 +431,7 @@ __device__ __forceinline__ void gru_bar_wait(uint32_t bar, uint32_t parity) {
         "GRU_DONE_%=:\n\t}"
         :: "r"(bar), "r"(parity) : "memory");
 }
+template <bool FAST>
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(256)
 gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ whh /*[2,768,256]*/, const float* __restrict__ bhh /*[2,768]*/,
               int T, float* __restrict__ out32 /*[T,512] or null*/, __half* __restrict__ out16 /*[T,512]*/) {
@@ -504,11 +505,18 @@ gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             sums[g] = a;
         }
-        // the gate math sits on the serial per-step chain: exp through ex2.approx (2 ulp), tanh(x) = 2 sigmoid(2x) - 1
-        // (absolute error ~1e-7, far below the fp16 operand rounding of the layers around the GRU)
-        const float r = __fdividef(1.f, 1.f + __expf(-(gir + sums[0] + b_r)));
-        const float z = __fdividef(1.f, 1.f + __expf(-(giz + sums[1] + b_z)));
-        const float n = __fdividef(2.f, 1.f + __expf(-2.f * (gin + r * (sums[2] + b_n)))) - 1.f;
+        // the gate math sits on the serial per-step chain.  FAST (RVCB_GRU_FAST=1): exp through ex2.approx, tanh(x) = 2 sigmoid(2x) - 1;
+        // measured SLOWER than the libm forms (RMVPE alone 2.96 vs 2.72 ms, profiles/r2k_stage_timing.txt): the default stays libm
+        float r, z, n;
+        if (FAST) {
+            r = __fdividef(1.f, 1.f + __expf(-(gir + sums[0] + b_r)));
+            z = __fdividef(1.f, 1.f + __expf(-(giz + sums[1] + b_z)));
+            n = __fdividef(2.f, 1.f + __expf(-2.f * (gin + r * (sums[2] + b_n)))) - 1.f;
+        } else {
+            r = 1.f / (1.f + expf(-(gir + sums[0] + b_r)));
+            z = 1.f / (1.f + expf(-(giz + sums[1] + b_z)));
+            n = tanhf(gin + r * (sums[2] + b_n));
+        }
         const float hn = (1.f - z) * n + z * hprev;
         const float h0 = __shfl_sync(0xffffffffu, hn, 0), h1 = __shfl_sync(0xffffffffu, hn, 8);
         const float h2 = __shfl_sync(0xffffffffu, hn, 16), h3 = __shfl_sync(0xffffffffu, hn, 24);
@@ -745,8 +753,10 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     __half* gru_out = ar.alloc<__half>((size_t)T * 512);
     {
         static const bool v1 = [] { const char* e = getenv("RVCB_GRU"); return e && !strcmp(e, "barrier"); }();
+        static const bool fast = [] { const char* e = getenv("RVCB_GRU_FAST"); return e && e[0] == '1'; }();      // measured slower (below)
         if (v1) gru_kernel<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
-        else gru_kernel_v2<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        else if (fast) gru_kernel_v2<true><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        else gru_kernel_v2<false><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         KERNEL_CHECK();
         count_launch();
     }
