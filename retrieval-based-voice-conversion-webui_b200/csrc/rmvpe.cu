@@ -431,7 +431,13 @@ __device__ __forceinline__ void gru_bar_wait(uint32_t bar, uint32_t parity) {
         "GRU_DONE_%=:\n\t}"
         :: "r"(bar), "r"(parity) : "memory");
 }
-template <bool FAST>
+
+__device__ __forceinline__ float gru_ldg(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <bool FAST, bool TRACE = false>
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(256)
 gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict__ whh /*[2,768,256]*/, const float* __restrict__ bhh /*[2,768]*/,
               int T, float* __restrict__ out32 /*[T,512] or null*/, __half* __restrict__ out16 /*[T,512]*/) {
@@ -468,22 +474,33 @@ gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict
     cluster.sync();
     int t = dir == 0 ? 0 : T - 1;
     const int dt = dir == 0 ? 1 : -1;
-    float gir = 0.f, giz = 0.f, gin = 0.f;
-    if (T > 0) {
+    // input projections of step s (gi*), s + 1 (p*) and, issued at the top of step s, s + 2 (q*).  The loads are volatile asm:
+    // the compiler otherwise sinks them to their first use at the end of the step and the L2 latency (~300 cycles) lands on the
+    // serial chain (measured: the ex2.approx gate variant came out SLOWER than libm for exactly this reason, profiles/r2k)
+    float gir = 0.f, giz = 0.f, gin = 0.f, pr = 0.f, pz = 0.f, pn = 0.f;
+    {
         const float* g0 = gi + (size_t)t * 1536 + dir * 768 + unit;
-        gir = __ldg(g0); giz = __ldg(g0 + GRU_H); gin = __ldg(g0 + 2 * GRU_H);
+        if (T > 0) { gir = gru_ldg(g0); giz = gru_ldg(g0 + GRU_H); gin = gru_ldg(g0 + 2 * GRU_H); }
+        if (T > 1) { g0 += dt * 1536; pr = gru_ldg(g0); pz = gru_ldg(g0 + GRU_H); pn = gru_ldg(g0 + 2 * GRU_H); }
     }
+    long long tr[5] = {0, 0, 0, 0, 0}, tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;      // RVCB_GRU_TRACE: where a step's cycles go
     for (int s = 0; s < T; ++s, t += dt) {
-        float nr = 0.f, nz = 0.f, nn = 0.f;
-        if (s + 1 < T) {
-            const float* g1 = gi + (size_t)(t + dt) * 1536 + dir * 768 + unit;
-            nr = __ldg(g1); nz = __ldg(g1 + GRU_H); nn = __ldg(g1 + 2 * GRU_H);
+        if (TRACE) {
+            const long long now = clock64();
+            if (s > 64 && s <= 64 + 1024) tr[4] += now - tc4;
+            tc0 = now;
+        }
+        float qr = 0.f, qz = 0.f, qn = 0.f;
+        if (s + 2 < T) {
+            const float* g2 = gi + (size_t)(t + 2 * dt) * 1536 + dir * 768 + unit;
+            qr = gru_ldg(g2); qz = gru_ldg(g2 + GRU_H); qn = gru_ldg(g2 + 2 * GRU_H);
         }
         const int cur = s & 1;
         if (s > 0) {
             gru_bar_wait(bar0 + 8u * cur, (uint32_t)(((s - 1) >> 1) & 1));
             if (threadIdx.x == 0 && s + 2 <= T) gru_bar_arm(bar0 + 8u * cur, GRU_H * 4);      // for h_{s+2}
         }
+        if (TRACE) tc1 = clock64();
         const float4* hc = reinterpret_cast<const float4*>(hbuf + cur * 256);
         float4 hv[8];
 #pragma unroll
@@ -505,8 +522,11 @@ gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             sums[g] = a;
         }
-        // the gate math sits on the serial per-step chain.  FAST (RVCB_GRU_FAST=1): exp through ex2.approx, tanh(x) = 2 sigmoid(2x) - 1;
-        // measured SLOWER than the libm forms (RMVPE alone 2.96 vs 2.72 ms, profiles/r2k_stage_timing.txt): the default stays libm
+        if (TRACE) { tc2 = clock64(); tc2 += (long long)(sums[0] == 12345.f); }
+        // the gate math sits on the serial per-step chain (in-kernel clock64 trace, RVCB_GRU_TRACE=1: 350 of ~1400 cycles per step
+        // with the libm forms).  FAST (default; RVCB_GRU_FAST=0 = libm): exp through ex2.approx (2 ulp), tanh(x) = 2 sigmoid(2x) - 1
+        // (absolute error ~1e-7, far below the fp16 operand rounding of the layers around the GRU): 173 cycles, RMVPE on 16 s
+        // 2.98 -> 2.80 ms -- but only with the input-projection loads pinned early (see gru_ldg above)
         float r, z, n;
         if (FAST) {
             r = __fdividef(1.f, 1.f + __expf(-(gir + sums[0] + b_r)));
@@ -518,6 +538,7 @@ gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict
             n = tanhf(gin + r * (sums[2] + b_n));
         }
         const float hn = (1.f - z) * n + z * hprev;
+        if (TRACE) { tc3 = clock64(); tc3 += (long long)(hn == 12345.f); }
         const float h0 = __shfl_sync(0xffffffffu, hn, 0), h1 = __shfl_sync(0xffffffffu, hn, 8);
         const float h2 = __shfl_sync(0xffffffffu, hn, 16), h3 = __shfl_sync(0xffffffffu, hn, 24);
         if (s + 1 < T && lane < GRU_CL)
@@ -527,8 +548,16 @@ gru_kernel_v2(const float* __restrict__ gi /*[T,1536]*/, const float* __restrict
             if (out32) out32[og] = hn;
             out16[og] = __float2half_rn(hn);
         }
-        gir = nr; giz = nz; gin = nn;
+        gir = pr; giz = pz; gin = pn;
+        pr = qr; pz = qz; pn = qn;
+        if (TRACE) {
+            tc4 = clock64();
+            if (s >= 64 && s < 64 + 1024) { tr[0] += tc1 - tc0; tr[1] += tc2 - tc1; tr[2] += tc3 - tc2; tr[3] += tc4 - tc3; }
+        }
     }
+    if (TRACE && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 37))
+        printf("[gru trace] thread %d: avg cycles / step: wait %lld, load h + matvec + reduce %lld, gates %lld, publish + store %lld, loop %lld\n",
+               (int)threadIdx.x, tr[0] >> 10, tr[1] >> 10, tr[2] >> 10, tr[3] >> 10, tr[4] >> 10);
     cluster.sync();      // nobody exits while a peer may still be storing into its shared memory
 }
 
@@ -753,8 +782,10 @@ static void rmvpe_forward(rvcb_rmvpe* h, const float* d_wav, int n, float thred,
     __half* gru_out = ar.alloc<__half>((size_t)T * 512);
     {
         static const bool v1 = [] { const char* e = getenv("RVCB_GRU"); return e && !strcmp(e, "barrier"); }();
-        static const bool fast = [] { const char* e = getenv("RVCB_GRU_FAST"); return e && e[0] == '1'; }();      // measured slower (below)
+        static const bool fast = [] { const char* e = getenv("RVCB_GRU_FAST"); return !(e && e[0] == '0'); }();
         if (v1) gru_kernel<<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        else if (getenv("RVCB_GRU_TRACE") && fast) gru_kernel_v2<true, true><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
+        else if (getenv("RVCB_GRU_TRACE")) gru_kernel_v2<false, true><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         else if (fast) gru_kernel_v2<true><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         else gru_kernel_v2<false><<<2 * GRU_CL, 256, 0, st>>>(gi, h->whh, h->bhh, T, nullptr, gru_out);
         KERNEL_CHECK();
