@@ -98,6 +98,10 @@ int rvcb_upsample_protect(const float* d_feats, const float* d_feats0, int T_h, 
  * d_scratch: >= n_in/8000 + n_out/(tgt_sr/2) + 8 doubles. */
 int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio16k, int64_t n_in, float rms_mix_rate,
                   double* d_scratch, void* stream);
+/* change_rms alone (pipeline.py:349-350), without the peak scaling: for the resample_sr branch (pipeline.py:351-354), where the
+ * resampler runs between the mix and the scaling -- rvcb_rms_mix, rvcb_resample_sinc, then rvcb_post_mix(rate = 1) = scaling only. */
+int rvcb_rms_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio16k, int64_t n_in, float rms_mix_rate,
+                  double* d_scratch, void* stream);
 
 /* ---- input front end ----------------------------------------------------------------------
  * rvcb_host_filtfilt: HOST function (no GPU): scipy.signal.filtfilt(b, a, x) with its defaults (odd extension,

@@ -147,7 +147,12 @@ class OraclePipeline:
         if rms_mix_rate != 1:
             audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
         if tgt_sr != resample_sr >= 16000:
-            raise NotImplementedError("librosa.resample is not restated (SURVEY §8f-2)")
+            # pipeline.py:351-354 calls librosa.resample (soxr_hq), which is not installed in the build container and whose
+            # arithmetic lives in a C library outside /root/reference: PARITY UNPINNED for this optional branch.  The stand-in is
+            # torchaudio's windowed-sinc resampler (sinc_interp_hann defaults), the library the reference itself uses for its other
+            # resamplers (gui.py:851-866); the product runs the same table as a CUDA kernel.
+            import torchaudio
+            audio_opt = torchaudio.functional.resample(torch.from_numpy(audio_opt.astype(np.float32)), tgt_sr, resample_sr).numpy()
         audio_max = np.abs(audio_opt).max() / 0.99
         max_int16 = 32768
         if audio_max > 1:

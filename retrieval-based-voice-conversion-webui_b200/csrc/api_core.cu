@@ -112,6 +112,14 @@ extern "C" int rvcb_post_mix(float* d_wav, int64_t n_out, int tgt_sr, const floa
     RVCB_API_END
 }
 
+extern "C" int rvcb_rms_mix(float* d_wav, int64_t n_out, int tgt_sr, const float* d_audio16k, int64_t n_in, float rms_mix_rate,
+                            double* d_scratch, void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_wav && d_audio16k && d_scratch && n_out > 0 && n_in > 0 && tgt_sr >= 16000, "bad argument");
+    rvcb::post_mix(d_wav, n_out, tgt_sr, d_audio16k, n_in, rms_mix_rate, d_scratch, (cudaStream_t)stream, false);
+    RVCB_API_END
+}
+
 // scipy.signal.lfilter's float64 loop (direct form II transposed), one pass; z is the state, updated in place.
 // NC known at compile time keeps the state in registers (the recurrence is one add -> mul -> sub dependency chain per sample).
 template <int NC>

@@ -551,7 +551,7 @@ __global__ void peak_scale_kernel(float* __restrict__ y, long n, const unsigned 
     y[i] *= sc;
 }
 
-void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s) {
+void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s, bool scale) {
     const int hop1 = 16000 / 2, hop2 = sr2 / 2;
     const int nf1 = 1 + (int)(n1 / hop1), nf2 = 1 + (int)(n2 / hop2);         // 1 + (len + 2*hop - 2*hop)/hop
     double* s1 = scratch;
@@ -566,9 +566,9 @@ void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate
         count_launch(2);
     }
     rms_mix_kernel<<<(unsigned)ceil_div_l(n2, 256), 256, 0, s>>>(y, n2, s1, nf1, 2 * hop1, s2, nf2, 2 * hop2, rate, do_mix, amax);
-    peak_scale_kernel<<<(unsigned)ceil_div_l(n2, 256), 256, 0, s>>>(y, n2, amax);
+    if (scale) peak_scale_kernel<<<(unsigned)ceil_div_l(n2, 256), 256, 0, s>>>(y, n2, amax);
     KERNEL_CHECK();
-    count_launch(2);
+    count_launch(scale ? 2 : 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ void upsample_protect(const float* feats, const float* feats0, int T_h, int C, c
 
 // RMS-envelope mix of the converted audio with the input's envelope + peak normalisation to the int16 range, in place on y
 // (pipeline.py:26-45, 349-360).  scratch: >= (n1/8000 + n2/(sr2/2) + 8) doubles.
-void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s);
+void post_mix(float* y, long n2, int sr2, const float* x16k, long n1, float rate, double* scratch, cudaStream_t s, bool scale = true);
 
 // fp32 SIMT GEMM  C[M,N] = A[M,K] * B[N,K]^T  (A rows may overlap: lda < K is allowed)
 void sgemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, cudaStream_t s);

@@ -70,6 +70,7 @@ class Pipeline(object):
         self.f0_gen = Generator(rmvpe_root, self.is_half, self.x_pad, self.device, self.window, self.sr)
         self._index_cache = {}
         self._side = torch.cuda.Stream(device=self.device)
+        self._resamplers = {}          # (tgt_sr, resample_sr) -> device sinc table of the resample_sr branch
         # RMVPE ends in the serial BiGRU and is the longer front branch: it gets a high-priority stream so that its CTAs are placed
         # first whenever SMs free up, and HuBERT + retrieval fill the rest (RVCB_F0_PRIO=0: RMVPE stays on the caller's stream)
         self._f0_stream = torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("RVCB_F0_PRIO", "1") != "0" else None
@@ -197,8 +198,25 @@ class Pipeline(object):
         slot[1].record(torch.cuda.current_stream())
         return x
 
+    def _epilogue_dev(self, out, tgt_sr, resample_sr, a16, rms_mix_rate):
+        """pipeline.py:349-360 on the device: change_rms, the optional resample_sr branch, peak normalisation to the int16 range.
+        The reference resamples with librosa (soxr), which is not installed here: the windowed-sinc resampler of torchaudio
+        (``torchaudio.functional.resample`` defaults) stands in, as a CUDA kernel (rvcb_resample_sinc) -- not numerically equal to
+        the reference on this optional branch."""
+        out = out.contiguous()
+        if not (tgt_sr != resample_sr >= 16000):
+            return engine.post_mix(out, tgt_sr, a16, rms_mix_rate)
+        if rms_mix_rate != 1:
+            out = engine.rms_mix(out, tgt_sr, a16, rms_mix_rate)
+        key = (int(tgt_sr), int(resample_sr))
+        if key not in self._resamplers:
+            k, width, up, down = engine.sinc_resample_kernel(tgt_sr, resample_sr)
+            self._resamplers[key] = (k.to(self.device), width, up, down)
+        out = engine.sinc_resample(out, *self._resamplers[key])
+        return engine.post_mix(out, resample_sr, a16, 1.0)            # rate 1: no mix, peak scaling only
+
     def _dev_body(self, x, model, net_g, sid, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version,
-                  protect, as_int16):
+                  protect, as_int16, resample_sr=0):
         """Device-resident body of one single-chunk utterance: x f32[n] (device) -> waveform (device).  No host
         synchronisation anywhere, so it can run eagerly or be captured once into a CUDA graph and replayed."""
         capturing = torch.cuda.is_current_stream_capturing()
@@ -244,11 +262,11 @@ class Pipeline(object):
                 audio_pad.record_stream(self._side)
             self._prefetched = (audio_pad, f, f_raw, ev)
         out = self._vc_dev(model, net_g, sid, audio_pad, pitch, pitchf, times, index, big_npy, index_rate, version, protect, trim=True)
-        out = engine.post_mix(out.contiguous(), tgt_sr, a16, rms_mix_rate)
+        out = self._epilogue_dev(out, tgt_sr, resample_sr, a16, rms_mix_rate)
         return engine.f32_to_i16(out) if as_int16 else out
 
     def _pipeline_single_dev(self, model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
-                             rms_mix_rate, version, protect, as_int16=False):
+                             rms_mix_rate, version, protect, as_int16=False, resample_sr=0):
         """One-chunk utterance with NO host round trip between the input copy and the result copy: high-pass filtfilt
         (pipeline.py:221), reflect padding (:241), RMVPE, f0 post-processing (rvc/f0/gen.py:10-41), HuBERT + retrieval on a
         side stream, synthesizer, RMS mix + scaling (:349-360) and the int16 cast (modules.py:181) all run on the device.
@@ -257,12 +275,13 @@ class Pipeline(object):
         t0 = time()
         host_ok = getattr(net_g, "accepts_host_scalars", False)
         sid_t = torch.tensor(sid).unsqueeze(0).long() if host_ok else torch.tensor(sid, device=self.device).unsqueeze(0).long()
-        args = (model, net_g, sid_t, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version, protect, as_int16)
+        args = (model, net_g, sid_t, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr, rms_mix_rate, version, protect, as_int16,
+                int(resample_sr))
         x = self._stage_h2d(audio)
         key = None
         if host_ok and os.environ.get("RVCB_GRAPHS", "1") != "0" and (index is None or isinstance(index, engine.Index)):
             key = (int(audio.shape[0]), id(model), id(net_g), int(sid), float(f0_up_key), id(index), float(index_rate), int(if_f0),
-                   int(tgt_sr), float(rms_mix_rate), str(version), float(protect), bool(as_int16))
+                   int(tgt_sr), float(rms_mix_rate), str(version), float(protect), bool(as_int16), int(resample_sr))
         ent = self._graphs.get(key) if key is not None else None
         if ent is not None and "graph" not in ent and not ent.get("failed"):
             # second sighting: capture (arenas and kernels are warm from the first run)
@@ -305,10 +324,10 @@ class Pipeline(object):
                 index = big_npy = None
         single = audio.shape[0] + 2 * (self.window // 2) <= self.t_max          # pipeline.py:224: no silence-point chunking
         if (single and if_f0 in (0, 1) and (if_f0 == 0 or f0_method == "rmvpe") and not hasattr(f0_file, "name")
-                and not (tgt_sr != resample_sr >= 16000) and not getattr(self, "_force_host", False)):
+                and not getattr(self, "_force_host", False)):
             as_i16 = getattr(self, "_want_int16", False)
             out = self._pipeline_single_dev(model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
-                                            rms_mix_rate, version, protect, as_int16=as_i16)
+                                            rms_mix_rate, version, protect, as_int16=as_i16, resample_sr=resample_sr)
             return out.cpu().numpy()
         audio = engine.host_filtfilt(bh, ah, zi_h, audio)       # == signal.filtfilt(bh, ah, audio), bit for bit
         audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
@@ -370,19 +389,6 @@ class Pipeline(object):
                                  (pitchf[:, t // W:] if t is not None else pitchf) if if_f0 else None,
                                  times, index, big_npy, index_rate, version, protect, trim=True))
         audio_dev = audio_opt[0] if len(audio_opt) == 1 else torch.cat(audio_opt)
-        if not (tgt_sr != resample_sr >= 16000):
-            # RMS-envelope mix + peak normalisation on the device (pipeline.py:349-360), then ONE D2H copy of the result
-            a16 = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(self.device, non_blocking=True)
-            audio_dev = engine.post_mix(audio_dev.contiguous(), tgt_sr, a16, rms_mix_rate)
-            return audio_dev.cpu().numpy()
-        audio_opt = audio_dev.cpu().numpy()
-        if rms_mix_rate != 1:
-            audio_opt = change_rms(audio, 16000, audio_opt, tgt_sr, rms_mix_rate)
-        import torchaudio          # librosa.resample (pipeline.py:351-354) is not installed; this branch stays on the host
-        audio_opt = torchaudio.functional.resample(torch.from_numpy(audio_opt.astype(np.float32)), tgt_sr, resample_sr).numpy()
-        audio_max = np.abs(audio_opt).max() / 0.99
-        max_int16 = 32768
-        if audio_max > 1:
-            max_int16 /= audio_max
-        audio_opt = audio_opt * max_int16
-        return audio_opt
+        # RMS-envelope mix (+ resample_sr branch) + peak normalisation on the device (pipeline.py:349-360), then ONE D2H copy
+        a16 = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).to(self.device, non_blocking=True)
+        return self._epilogue_dev(audio_dev, tgt_sr, resample_sr, a16, rms_mix_rate).cpu().numpy()

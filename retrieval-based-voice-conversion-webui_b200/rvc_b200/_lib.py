@@ -86,6 +86,7 @@ SIGNATURES = {
     "rvcb_flat_destroy": (None, [_P]),
     "rvcb_upsample_protect": (_I, [_P, _P, _I, _I, _P, _I, _F, _P, _P]),
     "rvcb_post_mix": (_I, [_P, _L, _I, _P, _L, _F, _P, _P]),
+    "rvcb_rms_mix": (_I, [_P, _L, _I, _P, _L, _F, _P, _P]),
     "rvcb_host_filtfilt": (_I, [_P, _P, _P, _I, _P, _I, _L, _P]),
     "rvcb_sosfiltfilt": (_I, [_P, _P, _I, _I, _P, _L, _P, _P, _P]),
     "rvcb_reflect_pad": (_I, [_P, _L, _L, _P, _P]),

@@ -218,6 +218,15 @@ def post_mix(wav: torch.Tensor, tgt_sr: int, audio16k: torch.Tensor, rms_mix_rat
     return wav
 
 
+def rms_mix(wav: torch.Tensor, tgt_sr: int, audio16k: torch.Tensor, rms_mix_rate: float) -> torch.Tensor:
+    """In place on ``wav``: the RMS-envelope mix alone (pipeline.py:349-350), no peak scaling (rvcb_rms_mix)."""
+    wav = _chk_dev(wav.reshape(-1), torch.float32, "wav")
+    a = _chk_dev(audio16k.reshape(-1), torch.float32, "audio16k")
+    scratch = torch.empty(a.numel() // 8000 + wav.numel() // (tgt_sr // 2) + 16, device=wav.device, dtype=torch.float64)
+    _lib.check(_lib.lib().rvcb_rms_mix(_p(wav), wav.numel(), int(tgt_sr), _p(a), a.numel(), float(rms_mix_rate), _p(scratch), _stream_ptr()))
+    return wav
+
+
 def rt_tail(infer_wav: torch.Tensor, input_wav: Optional[torch.Tensor], zc: int, rms_mix_rate: float, sola_buffer: torch.Tensor,
             block_frame: int, sola_search_frame: int, want_offset: bool = False):
     """gui.py:1024-1087 on the device: envelope mix (in place on ``infer_wav``) + SOLA.  Updates ``sola_buffer`` in place and

@@ -65,6 +65,44 @@ def test_pipeline_matches_oracle_with_shared_pitch_and_noise():
     assert np.median(np.abs(f2[: len(pitchf)][both] / pitchf[both] - 1)) < 1e-2
 
 
+def test_resample_sr_branch_on_the_device():
+    """pipeline.py:351-354 (resample_sr != tgt_sr): change_rms, resampler and peak scaling stay on the device (rvcb_rms_mix ->
+    rvcb_resample_sinc -> rvcb_post_mix(rate 1)) in both the single-chunk graph path and the host-chunking path; compared with the
+    oracle pipeline, whose stand-in for librosa's soxr resampler is torchaudio's sinc resampler (parity unpinned for this branch)."""
+    from infer.modules.vc.pipeline import Pipeline
+    from infer.modules.vc.utils import HubertB200
+    from rvc.synthesizer import get_synthesizer
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, audio, idx = _setup()
+    cfg = Cfg()
+    cfg.rmvpe_state_dict = rw
+    op = OP.OraclePipeline(48000, 1, 6, 38, 41, hw, rw, sw, OW.V2_48K_CONFIG, noise_seed=3)
+    with torch.no_grad():
+        ref = op.pipeline(0, audio.copy(), 0, "rmvpe", idx, 0.75, 1, 48000, 44100, 0.25, "v2", 0.33)
+    pitch, pitchf = op.pitch[0].numpy(), op.pitchf[0].numpy()
+    pipe = Pipeline(48000, cfg)
+    hub = HubertB200(hw, "cuda:0")
+    net_g, cpt = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
+    gidx = Index.from_oracle_layout(idx)
+    n48 = len(audio) * 3
+    assert ref.shape[0] == -(-n48 * 147 // 160)                 # ceil(n_48k * 44100 / 48000)
+    for force_host in (True, False):
+        pipe._force_host = force_host            # True: the reference's chunking control flow (shared f0); False: device-resident path
+        net_g.set_noise(*op.taps[0]["noise"])
+        f0 = (pitch, pitchf.astype(np.float64)) if force_host else "rmvpe"
+        out = pipe.pipeline(hub, net_g, 0, audio.copy(), [0, 0, 0], 0, f0, gidx, 0.75, 2 if force_host else 1, 3, 48000, 44100, 0.25,
+                            "v2", 0.33)
+        assert out.shape == ref.shape, (out.shape, ref.shape)
+        if force_host:
+            err = np.abs(out - ref).max() / 32768.0
+            print(f"[parity] resample_sr 44100 (shared f0 + noise): e2e max abs err {err:.3e}")
+            assert err < 1.5e-3, err
+        else:
+            rms = float(np.sqrt(np.mean((out - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
+            print(f"[parity] resample_sr 44100 (device-resident, own RMVPE): rel RMS err {rms:.3e}")
+            assert rms < 2e-2, rms
+
+
 def test_vc_facade_and_realtime_engine_run():
     from infer.lib.rtrvc import RVC
     from infer.modules.vc.modules import VC
