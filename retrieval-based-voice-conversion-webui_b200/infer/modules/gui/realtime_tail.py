@@ -7,8 +7,8 @@ this object carries the callback's block geometry (gui.py:783-855) and its SOLA 
     y = rvc.infer(input_wav_res, tail.block_frame_16k, tail.skip_head, tail.return_length, "rmvpe")
     out = tail.process(y, input_wav[tail.extra_frame:], rms_mix_rate)        # f32 [block_frame] on the device
 
-Not built: TorchGate input / output noise reduction (gui.py:974-993, 1015-1023; off by default) and the phase-vocoder
-cross-fade (use_pv, off by default).
+The rest of the callback's device side (input rings, TorchGate noise reduction, resamplers) is ``RealtimeBlock`` in
+realtime_block.py, which owns one of these; the phase-vocoder cross-fade (use_pv, off by default) is not built.
 """
 from __future__ import annotations
 

@@ -84,8 +84,7 @@ def test_resample_sr_branch_on_the_device():
     hub = HubertB200(hw, "cuda:0")
     net_g, cpt = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
     gidx = Index.from_oracle_layout(idx)
-    n48 = len(audio) * 3
-    assert ref.shape[0] == -(-n48 * 147 // 160)                 # ceil(n_48k * 44100 / 48000)
+    assert ref.shape[0] == -(-95040 * 147 // 160)               # ceil(n_48k * 44100 / 48000), n_48k = (2 * 199 - 200) * 480
     for force_host in (True, False):
         pipe._force_host = force_host            # True: the reference's chunking control flow (shared f0); False: device-resident path
         net_g.set_noise(*op.taps[0]["noise"])
