@@ -111,3 +111,42 @@ def test_end_to_end_with_shared_pitch_and_noise(world):
     assert out.shape == world["ref"].shape
     err = np.abs(out - world["ref"]).max() / 32768.0
     assert err <= 1e-3, f"end-to-end max abs err (full scale) {err}"
+
+
+def test_config1_shapes_v1_40k_no_index_precomputed_f0():
+    """BASELINE config #1 (the reference's own CPU-runnable case): one 10 s utterance, v1 / 40k synthesizer
+    (configs/v1/40k.json, upsampling [10, 10, 2, 2]), HuBERT layer 9 + final_proj -> 256-d, no index, f0 passed in pre-computed
+    (if_f0 = 2: parselmouth is absent), fp32 config (x_pad = 1): 192 000 padded samples, 599 HuBERT frames, T = 1198,
+    479 200 -> 399 200 output samples.  End to end against the fp32 CPU oracle with shared noise."""
+    from infer.modules.vc.pipeline import Pipeline
+    from infer.modules.vc.utils import HubertB200
+    from oracle import pipeline as OP, rmvpe as ORM, weights as OW
+    from rvc.synthesizer import get_synthesizer
+
+    class Cfg1:
+        x_pad, x_query, x_center, x_max, is_half = 1, 6, 38, 41, False
+        device = "cuda:0"
+        rmvpe_state_dict = None
+
+    torch.set_num_threads(min(32, max(8, torch.get_num_threads())))
+    hw = OW.hubert_weights(777)
+    sw = OW.synth_weights(1234, OW.V1_40K_CONFIG, 256)
+    audio = OW.synth_voice(10.0, seed=4).numpy()
+    p_len = (160000 + 2 * 16000) // 160
+    f0 = 110.0 + 220.0 * np.linspace(0.0, 1.0, p_len) ** 2
+    f0[(np.arange(p_len) // 100) % 5 == 4] = 0.0                       # unvoiced stretches
+    pitch, pitchf = ORM.post_process(f0.copy(), 0)
+    op = OP.OraclePipeline(40000, 1, 6, 38, 41, hw, None, sw, OW.V1_40K_CONFIG, noise_seed=5)
+    with torch.no_grad():
+        ref = op.pipeline(0, audio.copy(), 0, (pitch, pitchf), None, 0.0, 2, 40000, 0, 1.0, "v1", 0.33)
+    assert op.taps[0]["feats_hubert"].shape[1:] == (599, 256) and op.taps[0]["phone"].shape[1] == 1198 and ref.shape[0] == 399200
+    pipe = Pipeline(40000, Cfg1())
+    hub = HubertB200(hw, "cuda:0")
+    net_g, cpt = get_synthesizer(OW.synth_cpt(1234, "v1"), "cuda:0")
+    net_g.set_noise(*op.taps[0]["noise"])
+    out = pipe.pipeline(hub, net_g, 0, audio.copy(), [0, 0, 0], 0, (pitch, np.asarray(pitchf, dtype=np.float64)), "", 0.0, 2, 3, 40000, 0, 1.0,
+                        "v1", 0.33)
+    assert out.shape == ref.shape
+    err = np.abs(out - ref).max() / 32768.0
+    print(f"[parity] config #1 (v1/40k, layer 9 + final_proj, no index, given f0): e2e max abs err {err:.3e}")
+    assert err < 1.5e-3, err

@@ -85,21 +85,33 @@ def test_resample_sr_branch_on_the_device():
     net_g, cpt = get_synthesizer(OW.synth_cpt(1234, "v2"), "cuda:0")
     gidx = Index.from_oracle_layout(idx)
     assert ref.shape[0] == -(-95040 * 147 // 160)               # ceil(n_48k * 44100 / 48000), n_48k = (2 * 199 - 200) * 480
-    for force_host in (True, False):
-        pipe._force_host = force_host            # True: the reference's chunking control flow (shared f0); False: device-resident path
+    # 1) the reference's chunking control flow (host DSP prologue, shared f0 + noise) with the device epilogue, vs the oracle
+    pipe._force_host = True
+    net_g.set_noise(*op.taps[0]["noise"])
+    out = pipe.pipeline(hub, net_g, 0, audio.copy(), [0, 0, 0], 0, (pitch, pitchf.astype(np.float64)), gidx, 0.75, 2, 3, 48000, 44100, 0.25,
+                        "v2", 0.33)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    err = np.abs(out - ref).max() / 32768.0
+    print(f"[parity] resample_sr 44100 (shared f0 + noise): e2e max abs err {err:.3e}")
+    assert err < 1.5e-3, err
+    # 2) the device-resident single-chunk path (own RMVPE, eager then captured graph): same utterance without resampling, resampled
+    #    on the host by torchaudio and peak-scaled like pipeline.py:356-360, must equal the device branch
+    import torchaudio
+    pipe._force_host = False
+    outs = {}
+    for rs in (0, 44100, 44100, 44100):                       # the 3rd / 4th call with the same key capture and replay the graph
+        net_g._noise.clear()
         net_g.set_noise(*op.taps[0]["noise"])
-        f0 = (pitch, pitchf.astype(np.float64)) if force_host else "rmvpe"
-        out = pipe.pipeline(hub, net_g, 0, audio.copy(), [0, 0, 0], 0, f0, gidx, 0.75, 2 if force_host else 1, 3, 48000, 44100, 0.25,
-                            "v2", 0.33)
-        assert out.shape == ref.shape, (out.shape, ref.shape)
-        if force_host:
-            err = np.abs(out - ref).max() / 32768.0
-            print(f"[parity] resample_sr 44100 (shared f0 + noise): e2e max abs err {err:.3e}")
-            assert err < 1.5e-3, err
-        else:
-            rms = float(np.sqrt(np.mean((out - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
-            print(f"[parity] resample_sr 44100 (device-resident, own RMVPE): rel RMS err {rms:.3e}")
-            assert rms < 2e-2, rms
+        outs[rs] = pipe.pipeline(hub, net_g, 0, audio.copy(), [0, 0, 0], 0, "rmvpe", gidx, 0.75, 1, 3, 48000, rs, 1.0, "v2", 0.33)
+    net_g._noise.clear()
+    y = outs[0] / 32768.0
+    assert np.abs(outs[0]).max() < 0.98 * 32768                # unscaled regime: outs[0] = y * 32768 exactly
+    exp = torchaudio.functional.resample(torch.from_numpy(y.astype(np.float32)), 48000, 44100).numpy()
+    exp = exp * (32768 / max(1.0, np.abs(exp).max() / 0.99))
+    assert outs[44100].shape == exp.shape == ref.shape
+    err = np.abs(outs[44100] - exp).max() / 32768.0
+    print(f"[parity] resample_sr 44100 (device-resident, own RMVPE, graph replay) vs host torchaudio on the 48 kHz result: {err:.3e}")
+    assert err < 2e-5, err
 
 
 def test_vc_facade_and_realtime_engine_run():
