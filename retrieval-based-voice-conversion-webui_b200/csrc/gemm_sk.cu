@@ -248,14 +248,21 @@ bool gemm_sk_try(const GemmArgs& g, cudaStream_t stream) {
     // narrowest tile that still leaves the cluster grid within one wave; split 4-way when K is long enough, else 2-way.
     // Measured (profiles/r1x): 204x512, K = 4608: 25.8 -> 18.5 us; 1598x192, K = 2304: 20.8 -> 16.9 us; with fewer than 16
     // k-blocks per CTA the two cluster barriers cost more than the shorter K loop saves (3264x128, K = 1152: 15.9 -> 16.8 us).
+    // tuning knobs (measurement only): RVCB_SK_MAX = largest cluster tried (8 / 4 / 2), RVCB_SK_MINKB = fewest k-blocks per CTA,
+    // RVCB_SK_BN64 = 1 tries the 64-wide tile first
+    static const int sk_max = [] { const char* e = getenv("RVCB_SK_MAX"); return e ? atoi(e) : 4; }();
+    static const int min_kb = [] { const char* e = getenv("RVCB_SK_MINKB"); return e ? atoi(e) : 16; }();
+    static const bool bn64_first = [] { const char* e = getenv("RVCB_SK_BN64"); return e && e[0] == '1'; }();
     int BN = 0, SK = 0;
-    for (int bn : {32, 64}) {
+    const int bn_order[2] = {bn64_first ? 64 : 32, bn64_first ? 32 : 64};
+    for (int bi = 0; bi < 2 && !BN; ++bi) {
+        const int bn = bn_order[bi];
         if (bn > round_up(g.N, 32)) continue;
         const int tiles = m_tiles * ceil_div(g.N, bn);
-        for (int sk : {4, 2}) {
-            if (tiles * sk <= 148 && total_kb >= 16 * sk) { BN = bn; SK = sk; break; }
+        for (int sk : {8, 4, 2}) {
+            if (sk > sk_max) continue;
+            if (tiles * sk <= 148 && total_kb >= min_kb * sk) { BN = bn; SK = sk; break; }
         }
-        if (BN) break;
     }
     if (!BN) return false;
     if (g.conv2d_W) {

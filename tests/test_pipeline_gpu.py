@@ -272,6 +272,42 @@ def test_vc_multi_lanes_equal_the_serial_loop(tmp_path, monkeypatch):
     assert not np.array_equal(results[1][0], results[1][1])
 
 
+def test_long_single_chunk_utterance_runs_twice():
+    """A 45 s utterance at the GPU config's x_pad = 3 stays one chunk (t_max = 65 s): 51 s of model compute, 2549 HuBERT frames,
+    T = 5098 synthesizer frames -- larger than any shape the parity tests use (arena growth, M-keyed dispatch, attention over 5 k
+    frames).  No oracle at this size (the CPU path needs minutes): the output must be finite, non-silent, of the reference's length,
+    and the second call (captured graph) must reproduce the first with the noise pinned."""
+    from infer.modules.vc.modules import VC
+    from infer.modules.vc.utils import HubertB200
+    from rvc_b200.engine import Index
+    OI, OP, OW, hw, rw, sw, _, idx = _setup(1.0, 2000)
+
+    class CfgH:
+        x_pad, x_query, x_center, x_max, is_half = 3, 10, 60, 65, True
+        device = "cuda:0"
+        rmvpe_state_dict = rw
+
+    vc = VC(CfgH())
+    vc.hubert_model = HubertB200(hw, "cuda:0")
+    vc.get_vc(OW.synth_cpt(1234, "v2"))
+    gidx = Index.from_oracle_layout(idx)
+    audio = OW.synth_voice(45.0, seed=8).numpy()
+    n_pad = 45 * 16000 + 2 * 48000
+    T = min(2 * ((n_pad - 400) // 320 + 1), n_pad // 160)
+    g = torch.Generator().manual_seed(4)
+    n1, n2 = torch.randn(1, 192, T, generator=g).cuda(), torch.randn(1, T * 480, 1, generator=g).cuda()
+    outs = []
+    for _ in range(3):
+        vc.net_g._noise.clear()
+        vc.net_g.set_noise(n1, n2)
+        info, (sr, wav) = vc.vc_single(0, audio.copy(), 0, None, "rmvpe", gidx, "", 0.75, 3, 0, 0.25, 0.33)
+        assert info.startswith("Success"), info
+        outs.append(wav)
+    vc.net_g._noise.clear()
+    assert sr == 48000 and outs[0].dtype == np.int16 and outs[0].shape[0] == (T - 600) * 480
+    assert np.abs(outs[0]).max() > 1000 and np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 def test_no_f0_model_through_the_facade_and_realtime_engine():
     """cpt["f0"] == 0 end to end: get_vc picks the no-f0 container (modules.py:87-99 class table), the pipeline skips
     RMVPE (pipeline.py:203) and passes pitch=None, rtrvc skips its pitch cache (rtrvc.py:if_f0)."""

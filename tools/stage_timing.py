@@ -64,6 +64,12 @@ def graph_time(name, fn, reps=20):
     return out
 
 
+if os.environ.get("ONLY_RMVPE"):
+    a16 = engine.sosfiltfilt(P.sos_h, P.sos_zi_h, 3 * max(len(P.ah), len(P.bh)), x_dev)
+    audio_pad = engine.reflect_pad(a16, pipe.t_pad)
+    graph_time("RMVPE + f0 post (alone, all SMs)", lambda: pipe.f0_gen.calculate_device(audio_pad, audio_pad.numel() // pipe.window, 0))
+    graph_time("HuBERT only", lambda: vc.hubert_model.extract_features(source=audio_pad.view(1, -1), padding_mask=None, output_layer=12))
+    sys.exit(0)
 if not os.environ.get("ONLY_STEP"):
     a16 = graph_time("prologue: sosfiltfilt", lambda: engine.sosfiltfilt(P.sos_h, P.sos_zi_h, 3 * max(len(P.ah), len(P.bh)), x_dev))
     audio_pad = graph_time("prologue: reflect_pad", lambda: engine.reflect_pad(a16, pipe.t_pad))
