@@ -133,6 +133,12 @@ int rvcb_f32_to_i16(const float* d_x, int64_t n, int16_t* d_out, void* stream);
 int rvcb_rt_tail(float* d_infer, int n, const float* d_input, int zc, float rms_mix_rate, float* d_sola_buffer, int block_frame,
                  int sola_buffer_frame, int sola_search_frame, float* d_out, float* d_scratch, int* d_offset, void* stream);
 
+/* The same with the phase-vocoder cross-fade of gui.py:27-48 in place of the sin^2 cross-fade (gui.py:1078-1083, use_pv = True):
+ * rfft of the windowed previous tail and new head, magnitudes added, phase advanced linearly from the old phase to the new one.
+ * use_pv = 0 is rvcb_rt_tail.  d_scratch: >= 2*(n/zc + 1) + sola_search_frame + 4 + 3*(sola_buffer_frame/2 + 1) + sola_buffer_frame. */
+int rvcb_rt_tail_pv(float* d_infer, int n, const float* d_input, int zc, float rms_mix_rate, float* d_sola_buffer, int block_frame,
+                    int sola_buffer_frame, int sola_search_frame, int use_pv, float* d_out, float* d_scratch, int* d_offset, void* stream);
+
 /* ---- realtime noise gate and resamplers around RVC.infer, per block, on the device -------------------------------------
  * rvcb_torchgate_*  replaces: infer/modules/gui/torchgate.py TorchGate.__init__ :33-70 / forward :217-280 (the torch.stft /
  * torch.istft branch; stationary mask :128-178 with or without a noise reference, non-stationary mask :180-215, mask smoothing

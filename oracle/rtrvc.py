@@ -19,7 +19,7 @@ Reference sites restated:
       RVC.infer, resampler2, output TorchGate against output_buffer                               gui.py:1002-1023
 librosa.feature.rms is restated (centred frames, zero padding) as in oracle/pipeline.py; TorchGate is oracle/torchgate.py (pinned
 to the reference class); the resamplers are torchaudio.transforms.Resample itself (the library the reference calls).  The
-phase-vocoder cross-fade (use_pv, off by default) is not restated.
+phase-vocoder cross-fade (use_pv, gui.py:27-48) is restated operation for operation (``phase_vocoder``).
 The formant-shift resampling branch (rtrvc.py:251-260, torchaudio Resample) is outside the oracle: tests use formant = 0.
 """
 from __future__ import annotations
@@ -104,10 +104,31 @@ def envelope_mix(infer_wav: torch.Tensor, input_wav: torch.Tensor, zc: int, rms_
     return infer_wav * torch.pow(rms1 / rms2, torch.tensor(1 - rms_mix_rate))
 
 
-class SolaTail:
-    """State + per-block step of gui.py:1057-1087 (SOLA from DDSP-SVC), without the phase vocoder."""
+def phase_vocoder(a: torch.Tensor, b: torch.Tensor, fade_out: torch.Tensor, fade_in: torch.Tensor) -> torch.Tensor:
+    """gui.py:27-48, operation for operation (the dtype of a / b decides the precision: float32 in the callback)."""
+    window = torch.sqrt(fade_out * fade_in)
+    fa = torch.fft.rfft(a * window)
+    fb = torch.fft.rfft(b * window)
+    absab = torch.abs(fa) + torch.abs(fb)
+    n = a.shape[0]
+    if n % 2 == 0:
+        absab[1:-1] *= 2
+    else:
+        absab[1:] *= 2
+    phia = torch.angle(fa)
+    phib = torch.angle(fb)
+    deltaphase = phib - phia
+    deltaphase = deltaphase - 2 * np.pi * torch.floor(deltaphase / 2 / np.pi + 0.5)
+    w = 2 * np.pi * torch.arange(n // 2 + 1).to(a) + deltaphase
+    t = torch.arange(n).unsqueeze(-1).to(a) / n
+    return a * (fade_out ** 2) + b * (fade_in ** 2) + torch.sum(absab * torch.cos(w * t + phia), -1) * window / n
 
-    def __init__(self, block_frame: int, sola_buffer_frame: int, sola_search_frame: int):
+
+class SolaTail:
+    """State + per-block step of gui.py:1057-1087 (SOLA from DDSP-SVC); ``use_pv`` = the phase-vocoder branch (:1078-1083)."""
+
+    def __init__(self, block_frame: int, sola_buffer_frame: int, sola_search_frame: int, use_pv: bool = False):
+        self.use_pv = use_pv
         self.block_frame, self.sola_buffer_frame, self.sola_search_frame = block_frame, sola_buffer_frame, sola_search_frame
         self.sola_buffer = torch.zeros(sola_buffer_frame)
         self.fade_in, self.fade_out = fade_windows(sola_buffer_frame)
@@ -119,8 +140,11 @@ class SolaTail:
         cor_den = torch.sqrt(F.conv1d(conv_input ** 2, torch.ones(1, 1, self.sola_buffer_frame)) + 1e-8)
         sola_offset = int(torch.argmax(cor_nom[0, 0] / cor_den[0, 0]))
         infer_wav = infer_wav[sola_offset:]
-        infer_wav[: self.sola_buffer_frame] *= self.fade_in
-        infer_wav[: self.sola_buffer_frame] += self.sola_buffer * self.fade_out
+        if self.use_pv:
+            infer_wav[: self.sola_buffer_frame] = phase_vocoder(self.sola_buffer, infer_wav[: self.sola_buffer_frame], self.fade_out, self.fade_in)
+        else:
+            infer_wav[: self.sola_buffer_frame] *= self.fade_in
+            infer_wav[: self.sola_buffer_frame] += self.sola_buffer * self.fade_out
         self.sola_buffer[:] = infer_wav[self.block_frame: self.block_frame + self.sola_buffer_frame]
         return infer_wav[: self.block_frame].clone(), sola_offset
 

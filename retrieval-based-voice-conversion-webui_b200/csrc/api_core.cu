@@ -240,6 +240,16 @@ extern "C" int rvcb_rt_tail(float* d_infer, int n, const float* d_input, int zc,
     RVCB_API_END
 }
 
+extern "C" int rvcb_rt_tail_pv(float* d_infer, int n, const float* d_input, int zc, float rms_mix_rate, float* d_sola_buffer, int block_frame,
+                               int sola_buffer_frame, int sola_search_frame, int use_pv, float* d_out, float* d_scratch, int* d_offset,
+                               void* stream) {
+    RVCB_API_BEGIN
+    RVCB_CHECK(d_infer && d_sola_buffer && d_out && d_scratch, "null argument");
+    rvcb::rt_tail(d_infer, n, d_input, zc, rms_mix_rate, d_sola_buffer, block_frame, sola_buffer_frame, sola_search_frame, d_out, d_scratch,
+                  d_offset, (cudaStream_t)stream, use_pv != 0);
+    RVCB_API_END
+}
+
 extern "C" int rvcb_prof_classes(double* ms2, double* launches2, double* flops2, double* bytes2) {
     RVCB_API_BEGIN
     RVCB_CHECK(ms2 && launches2 && flops2 && bytes2, "null argument");

@@ -1002,7 +1002,7 @@ __device__ __forceinline__ float sola_fade_in(int i, int n) {      // sin(0.5*pi
 
 // one block: arg-max of the scores (first maximum), cross-fade, output block, new SOLA buffer
 __global__ void sola_finish_kernel(const float* __restrict__ y, const float* __restrict__ score, int nscore, float* __restrict__ buf, int nbuf,
-                                   int block, float* __restrict__ out, int* __restrict__ offset_out) {
+                                   int block, float* __restrict__ out, int* __restrict__ offset_out, const float* __restrict__ xf) {
     extern __shared__ float newbuf[];
     __shared__ float bv[32];
     __shared__ int bi[32], off_s;
@@ -1035,6 +1035,7 @@ __global__ void sola_finish_kernel(const float* __restrict__ y, const float* __r
     __syncthreads();
     const int off = off_s;
     auto faded = [&](int i) {          // element i of infer_wav[off:] after the in-place cross-fade of its first nbuf samples
+        if (i < nbuf && xf) return xf[i];                 // phase-vocoder cross-fade, computed by rt_pv_* from the same offset
         float v = y[off + i];
         if (i < nbuf) {
             const float fi = sola_fade_in(i, nbuf);
@@ -1048,8 +1049,94 @@ __global__ void sola_finish_kernel(const float* __restrict__ y, const float* __r
     for (int i = threadIdx.x; i < nbuf; i += blockDim.x) buf[i] = newbuf[i];
 }
 
+// ---- phase-vocoder cross-fade (gui.py:27-48, the use_pv branch of the callback) ----
+// offset = arg-max of the SOLA score (first maximum), for the kernels below
+__global__ void sola_argmax_kernel(const float* __restrict__ score, int nscore, int* __restrict__ off) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < nscore; i += blockDim.x) {
+        const float v = score[i];
+        if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+    for (int k = 16; k; k >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, k);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, k);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? bv[threadIdx.x] : -INFINITY;
+        idx = threadIdx.x < (blockDim.x >> 5) ? bi[threadIdx.x] : 0x7fffffff;
+        for (int k = 16; k; k >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, k);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, k);
+            if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+        }
+        if (threadIdx.x == 0) *off = idx == 0x7fffffff ? 0 : idx;
+    }
+}
+// One block per bin f: fa = rfft(a * w), fb = rfft(b * w), w = sqrt(fade_out * fade_in), a = sola_buffer, b = y[off : off + n].
+// spec[f] = (|fa| + |fb|) (x2 for the interior bins), spec[F + f] = angle(fa), spec[2F + f] = wrapped angle(fb) - angle(fa).
+__global__ void __launch_bounds__(128) rt_pv_dft_kernel(const float* __restrict__ a, const float* __restrict__ y, const int* __restrict__ off,
+                                                        int n, float* __restrict__ spec) {
+    __shared__ float red[4][4];
+    const int f = blockIdx.x, F = n / 2 + 1;
+    const float* b = y + *off;
+    float are = 0.f, aim = 0.f, bre = 0.f, bim = 0.f;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float fi = sola_fade_in(k, n);
+        const float w = sqrtf((1.f - fi) * fi);
+        const int r = (int)(((long)f * k) % n);
+        float sn, cs;
+        sincospif(2.f * (float)r / (float)n, &sn, &cs);
+        const float av = a[k] * w, bv = b[k] * w;
+        are = fmaf(av, cs, are); aim = fmaf(-av, sn, aim);
+        bre = fmaf(bv, cs, bre); bim = fmaf(-bv, sn, bim);
+    }
+    float v[4] = {are, aim, bre, bim};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        for (int o = 16; o; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t[4];
+        for (int j = 0; j < 4; ++j) t[j] = red[0][j] + red[1][j] + red[2][j] + red[3][j];
+        float mag = sqrtf(t[0] * t[0] + t[1] * t[1]) + sqrtf(t[2] * t[2] + t[3] * t[3]);
+        const bool interior = f >= 1 && ((n % 2 == 0) ? f < F - 1 : true);
+        if (interior) mag *= 2.f;
+        const float pa = atan2f(t[1], t[0]), pb = atan2f(t[3], t[2]);
+        float d = pb - pa;
+        d = d - 6.283185307179586f * floorf(d / 2.f / 3.141592653589793f + 0.5f);
+        spec[f] = mag; spec[F + f] = pa; spec[2 * F + f] = d;
+    }
+}
+// xf[i] = a[i] fo^2 + b[i] fi^2 + sum_f mag_f cos((2 pi f + d_f) i / n + pa_f) * w_i / n; the 2 pi f i / n part is reduced exactly.
+__global__ void rt_pv_synth_kernel(const float* __restrict__ a, const float* __restrict__ y, const int* __restrict__ off, int n,
+                                   const float* __restrict__ spec, float* __restrict__ xf) {
+    extern __shared__ float s_spec[];
+    const int F = n / 2 + 1;
+    for (int j = threadIdx.x; j < 3 * F; j += blockDim.x) s_spec[j] = spec[j];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float t = (float)i / (float)n;
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) {
+        const int r = (int)(((long)f * i) % n);
+        const float ph = 6.283185307179586f * ((float)r / (float)n) + s_spec[2 * F + f] * t + s_spec[F + f];
+        acc = fmaf(s_spec[f], cosf(ph), acc);
+    }
+    const float fi = sola_fade_in(i, n), fo = 1.f - fi;
+    xf[i] = a[i] * (fo * fo) + y[*off + i] * (fi * fi) + acc * sqrtf(fo * fi) / (float)n;
+}
+
 void rt_tail(float* infer, int n, const float* input, int zc, float rms_mix_rate, float* sola_buffer, int block_frame, int nbuf, int nsearch,
-             float* out, float* scratch, int* offset, cudaStream_t s) {
+             float* out, float* scratch, int* offset, cudaStream_t s, bool use_pv) {
     RVCB_CHECK(n >= block_frame + nbuf + nsearch && nbuf >= 1 && nbuf <= 8192 && zc >= 1, "rt_tail: bad sizes");
     const int nf = 1 + n / zc;
     float* rms = scratch;                       // [2, nf]
@@ -1061,7 +1148,25 @@ void rt_tail(float* infer, int n, const float* input, int zc, float rms_mix_rate
         count_launch(2);
     }
     sola_corr_kernel<<<nsearch + 1, 256, 0, s>>>(infer, sola_buffer, nbuf, score);
-    sola_finish_kernel<<<1, 1024, nbuf * sizeof(float), s>>>(infer, score, nsearch + 1, sola_buffer, nbuf, block_frame, out, offset);
+    const float* xf = nullptr;
+    if (use_pv) {
+        const int F = nbuf / 2 + 1;
+        int* off = reinterpret_cast<int*>(score + nsearch + 1);      // [1] (+1 pad)
+        float* spec = score + nsearch + 3;                            // [3, F]
+        float* x = spec + 3 * F;                                      // [nbuf]
+        RVCB_CHECK((size_t)3 * F * sizeof(float) <= 96 * 1024, "rt_tail: phase-vocoder frame too long");
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(rt_pv_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = true;
+        }
+        sola_argmax_kernel<<<1, 1024, 0, s>>>(score, nsearch + 1, off);
+        rt_pv_dft_kernel<<<F, 128, 0, s>>>(sola_buffer, infer, off, nbuf, spec);
+        rt_pv_synth_kernel<<<ceil_div(nbuf, 128), 128, (size_t)3 * F * sizeof(float), s>>>(sola_buffer, infer, off, nbuf, spec, x);
+        count_launch(3);
+        xf = x;
+    }
+    sola_finish_kernel<<<1, 1024, nbuf * sizeof(float), s>>>(infer, score, nsearch + 1, sola_buffer, nbuf, block_frame, out, offset, xf);
     KERNEL_CHECK();
     count_launch(2);
 }

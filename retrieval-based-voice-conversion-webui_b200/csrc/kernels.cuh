@@ -71,6 +71,6 @@ void f0_post(const float* f0, int n_frames, int p_len, double key_factor, double
 // Realtime tail of gui.py's audio callback on the device (gui.py:1024-1087): envelope mix (rms_mix_rate < 1, in place on
 // `infer`) + SOLA offset search, cross-fade, output block and buffer update.  scratch: >= 2 * (n / zc + 1) + nsearch + 1 floats.
 void rt_tail(float* infer, int n, const float* input, int zc, float rms_mix_rate, float* sola_buffer, int block_frame, int nbuf, int nsearch,
-             float* out, float* scratch, int* offset, cudaStream_t s);
+             float* out, float* scratch, int* offset, cudaStream_t s, bool use_pv = false);
 
 }  // namespace rvcb

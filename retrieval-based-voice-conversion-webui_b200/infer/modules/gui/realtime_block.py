@@ -4,7 +4,7 @@ cross-fade, resampling to 16 kHz, ``rtrvc.RVC.infer``, resampling back when the 
 volume-envelope mix, SOLA -- runs on the GPU as ONE CUDA graph per block (captured on the second block with the same settings),
 with one H2D copy of the block in and one D2H copy of ``block_frame`` samples out.  The GUI itself (FreeSimpleGUI, sounddevice,
 the audio process, device enumeration) is out of scope; the response-threshold gate (gui.py:951-966) works on the host block in
-numpy exactly where the reference has it.  Not built: the phase-vocoder cross-fade (use_pv, off by default).
+numpy exactly where the reference has it; ``use_pv`` selects the phase-vocoder cross-fade (gui.py:27-48, 1078-1083).
 
     blk = RealtimeBlock(rvc, samplerate=48000, block_time=0.16, crossfade_time=0.05, extra_time=2.5)
     out = blk.process(indata)            # np.float32 [block_frame] -> np.float32 [block_frame]
@@ -35,12 +35,12 @@ def _rms_frames(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray
 class RealtimeBlock:
     def __init__(self, rvc, samplerate: int = 48000, block_time: float = 0.25, crossfade_time: float = 0.05, extra_time: float = 2.5,
                  I_noise_reduce: bool = False, O_noise_reduce: bool = False, rms_mix_rate: float = 1.0, threhold: float = -60.0,
-                 f0method: str = "rmvpe", device="cuda:0"):
+                 f0method: str = "rmvpe", device="cuda:0", use_pv: bool = False):
         self.rvc, self.f0method = rvc, f0method
         self.device = torch.device(device if "cuda" in str(device) else "cuda:0")
         self.samplerate = samplerate
         self.I_noise_reduce, self.O_noise_reduce, self.rms_mix_rate, self.threhold = I_noise_reduce, O_noise_reduce, rms_mix_rate, threhold
-        t = self.tail = RealtimeTail(samplerate, block_time, crossfade_time, extra_time, self.device)
+        t = self.tail = RealtimeTail(samplerate, block_time, crossfade_time, extra_time, self.device, use_pv)
         self.zc, self.block_frame, self.block_frame_16k = t.zc, t.block_frame, t.block_frame_16k
         self.sola_buffer_frame, self.extra_frame = t.sola_buffer_frame, t.extra_frame
         self.skip_head, self.return_length = t.skip_head, t.return_length
@@ -126,7 +126,7 @@ class RealtimeBlock:
         if hin is None:
             hin = self._host_in[n] = torch.empty(n, dtype=torch.float32).pin_memory()
         hin.numpy()[:] = indata
-        key = (n, self.I_noise_reduce, self.O_noise_reduce, float(self.rms_mix_rate), self.f0method, float(self.rvc.f0_up_key),
+        key = (n, self.I_noise_reduce, self.O_noise_reduce, bool(self.tail.use_pv), float(self.rms_mix_rate), self.f0method, float(self.rvc.f0_up_key),
                float(self.rvc.formant_shift), float(self.rvc.index_rate), id(getattr(self.rvc, "index", None)))
         ent = self._graphs.get(key)
         use_graphs = os.environ.get("RVCB_GRAPHS", "1") != "0" and isinstance(self.f0method, str)

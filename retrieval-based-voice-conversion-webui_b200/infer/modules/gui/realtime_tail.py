@@ -8,7 +8,7 @@ this object carries the callback's block geometry (gui.py:783-855) and its SOLA 
     out = tail.process(y, input_wav[tail.extra_frame:], rms_mix_rate)        # f32 [block_frame] on the device
 
 The rest of the callback's device side (input rings, TorchGate noise reduction, resamplers) is ``RealtimeBlock`` in
-realtime_block.py, which owns one of these; the phase-vocoder cross-fade (use_pv, off by default) is not built.
+realtime_block.py, which owns one of these; the phase-vocoder cross-fade (use_pv, gui.py:27-48) is the ``use_pv`` flag.
 """
 from __future__ import annotations
 
@@ -22,7 +22,8 @@ from rvc_b200 import engine
 
 class RealtimeTail:
     def __init__(self, samplerate: int = 48000, block_time: float = 0.25, crossfade_time: float = 0.05, extra_time: float = 2.5,
-                 device="cuda:0"):
+                 device="cuda:0", use_pv: bool = False):
+        self.use_pv = use_pv                       # gui.py:1078-1083: phase-vocoder cross-fade instead of the sin^2 cross-fade
         self.device = torch.device(device if "cuda" in str(device) else "cuda:0")
         self.samplerate = samplerate
         self.zc = samplerate // 100                                                                           # gui.py:783
@@ -53,7 +54,7 @@ class RealtimeTail:
         if rms_mix_rate < 1 and input_wav is None:
             raise ValueError("rms_mix_rate < 1 needs input_wav")
         res = engine.rt_tail(infer_wav, input_wav if rms_mix_rate < 1 else None, self.zc, rms_mix_rate, self.sola_buffer, self.block_frame,
-                             self.sola_search_frame, want_offset)
+                             self.sola_search_frame, want_offset, self.use_pv)
         if want_offset:
             self.last_offset = res[1]
             return res[0]

@@ -62,6 +62,7 @@ SIGNATURES = {
     "rvcb_op_resblock1_out_rows": (_L, [_I, _I, C.POINTER(_I), _I]),
     "rvcb_op_resblock1": (_I, [_I, _I, C.POINTER(_I), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _I, _P, _P]),
     "rvcb_rt_tail": (_I, [_P, _I, _P, _I, _F, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "rvcb_rt_tail_pv": (_I, [_P, _I, _P, _I, _F, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rvcb_torchgate_create": (_I, [_I, _I, _I, _I, _F, _F, _F, _I, _F, _P, _I, _I, C.POINTER(_P)]),
     "rvcb_torchgate_out_len": (_L, [_P, _L]),
     "rvcb_torchgate_apply": (_I, [_P, _P, _L, _P, _L, _P, _P]),

@@ -228,7 +228,7 @@ def rms_mix(wav: torch.Tensor, tgt_sr: int, audio16k: torch.Tensor, rms_mix_rate
 
 
 def rt_tail(infer_wav: torch.Tensor, input_wav: Optional[torch.Tensor], zc: int, rms_mix_rate: float, sola_buffer: torch.Tensor,
-            block_frame: int, sola_search_frame: int, want_offset: bool = False):
+            block_frame: int, sola_search_frame: int, want_offset: bool = False, use_pv: bool = False):
     """gui.py:1024-1087 on the device: envelope mix (in place on ``infer_wav``) + SOLA.  Updates ``sola_buffer`` in place and
     returns the output block (and the offset tensor if asked)."""
     y = _chk_dev(infer_wav.reshape(-1), torch.float32, "infer_wav")
@@ -238,10 +238,12 @@ def rt_tail(infer_wav: torch.Tensor, input_wav: Optional[torch.Tensor], zc: int,
     x = None if input_wav is None else _chk_dev(input_wav.reshape(-1), torch.float32, "input_wav")
     n = y.numel()
     out = torch.empty(block_frame, device=y.device, dtype=torch.float32)
-    scratch = torch.empty(2 * (n // zc + 1) + sola_search_frame + 8, device=y.device, dtype=torch.float32)
+    nb = int(buf.numel())
+    scratch = torch.empty(2 * (n // zc + 1) + sola_search_frame + 8 + (3 * (nb // 2 + 1) + nb if use_pv else 0), device=y.device,
+                          dtype=torch.float32)
     off = torch.empty(1, device=y.device, dtype=torch.int32) if want_offset else None
-    _lib.check(_lib.lib().rvcb_rt_tail(_p(y), n, _p(x), int(zc), float(rms_mix_rate), _p(buf), int(block_frame), int(buf.numel()),
-                                       int(sola_search_frame), _p(out), _p(scratch), _p(off), _stream_ptr()))
+    _lib.check(_lib.lib().rvcb_rt_tail_pv(_p(y), n, _p(x), int(zc), float(rms_mix_rate), _p(buf), int(block_frame), nb,
+                                          int(sola_search_frame), int(bool(use_pv)), _p(out), _p(scratch), _p(off), _stream_ptr()))
     return (out, off) if want_offset else out
 
 
