@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "gemm.cuh"
 #include "../../include/rvcb200.h"
 #include "api_macros.h"
 
@@ -24,6 +25,17 @@ __global__ void tg_pad_kernel(const float* __restrict__ x, long n, int half, flo
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + 2L * half) return;
     xp[i] = (i >= half && i < half + n) ? x[i - half] : 0.f;                     // torch.stft(center=True, pad_mode="constant")
+}
+
+// Split-precision operands for the tensor-core DFTs (same scheme as RMVPE's mel front end, rmvpe.cu): v = hi + lo / 2048 with hi, lo
+// fp16.  Forward: the zero-padded signal as rows of `hop` samples, rows [0, R) = hi, rows [R, 2R) = lo.
+__global__ void tg_split_pad_kernel(const float* __restrict__ x, long n, int half, int R, int hop, __half* __restrict__ y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)R * hop) return;
+    const float v = (i >= half && i < half + n) ? x[i - half] : 0.f;
+    const __half hi = __float2half_rn(v);
+    y[i] = hi;
+    y[(long)R * hop + i] = __float2half_rn((v - __half2float(hi)) * 2048.f);
 }
 
 // spec: [T, 2F] (re | im).  One block = 32 bins x 8 time lanes.  mode 0: val[f, t] = max(dB, max_t dB - 40) (amp_to_db);
@@ -118,8 +130,10 @@ __global__ void tg_mask_kernel(const float* __restrict__ val, const float* __res
 }
 
 // Y[t, f] = X[t, f] * (filt (*) mask)[f, t]: conv2d(padding="same") of the mask with the fr x fc smoothing filter, zero outside.
+// y16 (optional, instead of y): the masked spectrum as split fp16 planes [2T, Kp] (rows [0, T) hi, [T, 2T) lo x 2048; columns
+// [2F, Kp) stay zero) for the tensor-core inverse DFT.
 __global__ void tg_smooth_apply_kernel(const float* __restrict__ spec, const float* __restrict__ mask, const float* __restrict__ filt,
-                                       int fr, int fc, int T, int F, float* __restrict__ y) {
+                                       int fr, int fc, int T, int F, float* __restrict__ y, __half* __restrict__ y16, int Kp) {
     extern __shared__ float s_f[];
     for (int i = threadIdx.x; i < fr * fc; i += blockDim.x) s_f[i] = filt[i];
     __syncthreads();
@@ -140,8 +154,17 @@ __global__ void tg_smooth_apply_kernel(const float* __restrict__ spec, const flo
             }
         }
     }
-    y[(long)t * 2 * F + f] = spec[(long)t * 2 * F + f] * s;
-    y[(long)t * 2 * F + F + f] = spec[(long)t * 2 * F + F + f] * s;
+    const float re = spec[(long)t * 2 * F + f] * s, im = spec[(long)t * 2 * F + F + f] * s;
+    if (y16) {
+        const __half rh = __float2half_rn(re), ih = __float2half_rn(im);
+        y16[(long)t * Kp + f] = rh;
+        y16[(long)t * Kp + F + f] = ih;
+        y16[(long)(T + t) * Kp + f] = __float2half_rn((re - __half2float(rh)) * 2048.f);
+        y16[(long)(T + t) * Kp + F + f] = __float2half_rn((im - __half2float(ih)) * 2048.f);
+    } else {
+        y[(long)t * 2 * F + f] = re;
+        y[(long)t * 2 * F + F + f] = im;
+    }
 }
 
 // torch.istft(center=True): overlap-add of the (already windowed) frames, divided by the overlap-added squared window, trimmed by n_fft/2.
@@ -191,9 +214,13 @@ struct rvcb_torchgate {
     int sr = 0, n_fft = 0, hop = 0, F = 0, nonstat = 0, n_move = 0, fr = 0, fc = 0;
     float prop = 1.f, n_std = 1.5f, n_thresh = 1.3f, temp = 0.1f;
     float *fwd = nullptr, *inv = nullptr, *w2 = nullptr, *filt = nullptr;
+    // tensor-core DFTs (bk != 0): fwd16 [2F, 3N] = (hi | lo | hi / 2048) of the forward basis, inv16 [N, 3 Kp] the same of N x the
+    // inverse basis (the 1 / N goes into the GEMM's alpha: the split halves stay in fp16's normal range), Kp = 2F rounded up to 64
+    __half *fwd16 = nullptr, *inv16 = nullptr;
+    int bk = 0, Kp = 0;
     Arena arena;
     ~rvcb_torchgate() {
-        cudaFree(fwd); cudaFree(inv); cudaFree(w2); cudaFree(filt);
+        cudaFree(fwd); cudaFree(inv); cudaFree(w2); cudaFree(filt); cudaFree(fwd16); cudaFree(inv16);
     }
 };
 
@@ -231,6 +258,37 @@ int rvcb_torchgate_create(int sr, int n_fft, int hop, int nonstationary, float n
         }
         h->fwd = dev_upload(fwd.data(), fwd.size());
         h->inv = dev_upload(inv.data(), inv.size());
+        {
+            static const bool fp32_only = [] { const char* e = getenv("RVCB_TG_FP32"); return e && e[0] == '1'; }();
+            const int rem = N % hop;
+            for (int bk : {32, 16})
+                if (!h->bk && !fp32_only && hop % bk == 0 && rem % bk == 0 && hop % 8 == 0 && N / hop + (rem ? 1 : 0) <= 32) h->bk = bk;
+        }
+        if (h->bk) {
+            h->Kp = round_up(2 * F, 64);
+            std::vector<__half> f16((size_t)2 * F * 3 * N), i16((size_t)N * 3 * h->Kp, __float2half(0.f));
+            auto split = [](float b, __half& hi, __half& lo, __half& hs) {
+                hi = __float2half_rn(b);
+                const float hf = __half2float(hi);
+                lo = __float2half_rn(b - hf);
+                hs = __float2half_rn(hf * (1.f / 2048.f));
+            };
+            for (int r = 0; r < 2 * F; ++r)
+                for (int n = 0; n < N; ++n) {
+                    __half hi, lo, hs;
+                    split(fwd[(size_t)r * N + n], hi, lo, hs);
+                    f16[(size_t)r * 3 * N + n] = hi; f16[(size_t)r * 3 * N + N + n] = lo; f16[(size_t)r * 3 * N + 2 * N + n] = hs;
+                }
+            for (int n = 0; n < N; ++n)
+                for (int j = 0; j < 2 * F; ++j) {
+                    __half hi, lo, hs;
+                    split(inv[(size_t)n * 2 * F + j] * (float)N, hi, lo, hs);
+                    __half* row = i16.data() + (size_t)n * 3 * h->Kp;
+                    row[j] = hi; row[h->Kp + j] = lo; row[2 * h->Kp + j] = hs;
+                }
+            h->fwd16 = dev_upload(f16.data(), f16.size());
+            h->inv16 = dev_upload(i16.data(), i16.size());
+        }
         h->w2 = dev_upload(w2.data(), w2.size());
         if (filter_rows) h->filt = dev_upload(h_filter, (size_t)filter_rows * filter_cols);
     } catch (...) {
@@ -253,6 +311,7 @@ int rvcb_torchgate_apply(rvcb_torchgate* h, const float* d_x, int64_t n, const f
     auto rnd = [](size_t b) { return (b + 1023) & ~size_t(1023); };
     size_t need = rnd((size_t)(n + N) * 4) + rnd((size_t)T * 2 * F * 4) * 2 + rnd((size_t)F * T * 4) * 2 + rnd((size_t)F * 4) + rnd((size_t)T * N * 4);
     if (d_xn) need += rnd((size_t)(n_noise + N) * 4) + rnd((size_t)Tn * 2 * F * 4);
+    if (h->bk) need += rnd((size_t)(n + N + 3L * hop) * 4 + 128) + rnd((size_t)(n_noise + N + 3L * hop) * 4 + 128) + rnd((size_t)2 * T * h->Kp * 2);
     h->arena.reserve(need + 4096);
     h->arena.reset();
     float* xp = h->arena.alloc<float>(n + N);
@@ -262,10 +321,34 @@ int rvcb_torchgate_apply(rvcb_torchgate* h, const float* d_x, int64_t n, const f
     float* mask = h->arena.alloc<float>((size_t)F * T);
     float* thresh = h->arena.alloc<float>(F);
     float* frames = h->arena.alloc<float>((size_t)T * N);
-    tg_pad_kernel<<<(unsigned)ceil_div_l(n + N, 256), 256, 0, st>>>(d_x, n, N / 2, xp);
-    KERNEL_CHECK();
-    count_launch();
-    sgemm_nt(xp, hop, h->fwd, N, spec, 2 * F, T, 2 * F, N, st);
+    // forward STFT: spec[t, :] = frame t x basis.  Tensor-core form: a frame is N / hop consecutive hop-sized rows of the padded signal
+    auto stft = [&](const float* x, long len, int frames, float* pad32, float* out) {
+        if (!h->bk) {
+            tg_pad_kernel<<<(unsigned)ceil_div_l(len + N, 256), 256, 0, st>>>(x, len, N / 2, pad32);
+            KERNEL_CHECK();
+            count_launch();
+            sgemm_nt(pad32, hop, h->fwd, N, out, 2 * F, frames, 2 * F, N, st);
+            return;
+        }
+        const int R = (int)ceil_div_l(len + N, hop) + 1;
+        __half* ws = h->arena.alloc<__half>((size_t)2 * R * hop + 64);
+        tg_split_pad_kernel<<<(unsigned)ceil_div_l((long)R * hop, 256), 256, 0, st>>>(x, len, N / 2, R, hop, ws);
+        KERNEL_CHECK();
+        count_launch();
+        GemmArgs g;
+        g.A = ws; g.lda = hop; g.a_rows = 2 * R; g.a_cols = hop;
+        g.B = h->fwd16; g.ldb = 3 * N; g.b_rows = 2 * F; g.b_cols = 3 * N;
+        g.M = frames; g.N = 2 * F; g.block_k = h->bk;
+        g.nseg = 0;
+        const int q = N / hop, rem = N % hop;
+        for (int part = 0; part < 3; ++part) {
+            for (int j = 0; j < q; ++j) g.seg[g.nseg++] = {(part == 2 ? R : 0) + j, 0, 0, hop / h->bk};
+            if (rem) g.seg[g.nseg++] = {(part == 2 ? R : 0) + q, 0, 0, rem / h->bk};
+        }
+        g.out32 = out; g.ld32 = 2 * F;
+        gemm(g, st);
+    };
+    stft(d_x, n, T, xp, spec);
     const int fb = ceil_div(F, 32);
     if (h->nonstat) {
         tg_db_kernel<<<fb, 256, 0, st>>>(spec, T, F, 1, 40.f, h->n_std, val, nullptr);
@@ -274,14 +357,12 @@ int rvcb_torchgate_apply(rvcb_torchgate* h, const float* d_x, int64_t n, const f
     } else if (d_xn) {
         float* np = h->arena.alloc<float>(n_noise + N);
         float* nspec = h->arena.alloc<float>((size_t)Tn * 2 * F);
-        tg_pad_kernel<<<(unsigned)ceil_div_l(n_noise + N, 256), 256, 0, st>>>(d_xn, n_noise, N / 2, np);
-        KERNEL_CHECK();
-        sgemm_nt(np, hop, h->fwd, N, nspec, 2 * F, Tn, 2 * F, N, st);
+        stft(d_xn, n_noise, Tn, np, nspec);
         tg_db_kernel<<<fb, 256, 0, st>>>(nspec, Tn, F, 0, 40.f, h->n_std, nullptr, thresh);
         KERNEL_CHECK();
         tg_db_kernel<<<fb, 256, 0, st>>>(spec, T, F, 0, 40.f, h->n_std, val, nullptr);
         KERNEL_CHECK();
-        count_launch(3);
+        count_launch(2);
     } else {
         tg_db_kernel<<<fb, 256, 0, st>>>(spec, T, F, 0, 40.f, h->n_std, val, thresh);
         KERNEL_CHECK();
@@ -290,10 +371,27 @@ int rvcb_torchgate_apply(rvcb_torchgate* h, const float* d_x, int64_t n, const f
     const long ft = (long)F * T;
     tg_mask_kernel<<<(unsigned)ceil_div_l(ft, 256), 256, 0, st>>>(val, thresh, T, F, h->nonstat, h->n_move, h->n_thresh, h->temp, h->prop, mask);
     KERNEL_CHECK();
-    tg_smooth_apply_kernel<<<(unsigned)ceil_div_l(ft, 256), 256, (size_t)h->fr * h->fc * 4, st>>>(spec, mask, h->filt, h->fr, h->fc, T, F, yspec);
+    __half* y16 = nullptr;
+    if (h->bk) {
+        y16 = h->arena.alloc<__half>((size_t)2 * T * h->Kp);
+        CUDA_CHECK(cudaMemsetAsync(y16, 0, (size_t)2 * T * h->Kp * sizeof(__half), st));       // the K padding columns
+    }
+    tg_smooth_apply_kernel<<<(unsigned)ceil_div_l(ft, 256), 256, (size_t)h->fr * h->fc * 4, st>>>(spec, mask, h->filt, h->fr, h->fc, T, F, yspec,
+                                                                                                   y16, h->Kp);
     KERNEL_CHECK();
     count_launch(2);
-    sgemm_nt(yspec, 2 * F, h->inv, 2 * F, frames, N, T, N, 2 * F, st);
+    if (!h->bk) sgemm_nt(yspec, 2 * F, h->inv, 2 * F, frames, N, T, N, 2 * F, st);
+    else {
+        GemmArgs g;
+        g.A = y16; g.lda = h->Kp; g.a_rows = 2 * T; g.a_cols = h->Kp;
+        g.B = h->inv16; g.ldb = 3 * h->Kp; g.b_rows = N; g.b_cols = 3 * h->Kp;
+        g.M = T; g.N = N; g.block_k = 64;
+        g.nseg = 3;
+        for (int part = 0; part < 3; ++part) g.seg[part] = {part == 2 ? T : 0, 0, 0, h->Kp / 64};
+        g.alpha = 1.f / (float)N;
+        g.out32 = frames; g.ld32 = N;
+        gemm(g, st);
+    }
     const long n_out = (long)hop * (T - 1);
     tg_ola_kernel<<<(unsigned)ceil_div_l(n_out, 256), 256, 0, st>>>(frames, h->w2, T, N, hop, n_out, d_y);
     KERNEL_CHECK();
