@@ -96,17 +96,27 @@ __global__ void hubert_conv0_kernel(const float* __restrict__ wav, int n_samples
     atomicAdd(&stats[512 + c], (double)s2);
 }
 
-__global__ void hubert_gn_gelu_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, __half* __restrict__ out, int T0) {
+// thread = channel (512), block = GN_TSTEP time steps: the per-channel mean / rstd (float64 divisions and a square root) are computed
+// once per thread instead of once per element (the per-element form ran at 1.2 TB/s: 135 us for 157 MB); same arithmetic per element
+constexpr int GN_TSTEP = 32;
+__global__ void __launch_bounds__(512) hubert_gn_gelu_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             __half* __restrict__ out, int T0) {
     pdl_trigger();
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)T0 * 512) return;
-    const int c = (int)(idx & 511);
+    const int c = threadIdx.x;
     const double mean = stats[c] / T0;
     const double var = stats[512 + c] / T0 - mean * mean;
     const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-    const float v = (y[idx] - (float)mean) * rstd * gamma[c] + beta[c];
-    out[idx] = __float2half_rn(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));
+    const float m = (float)mean, g = gamma[c], b = beta[c];
+    const int t0 = blockIdx.x * GN_TSTEP;
+#pragma unroll 4
+    for (int tt = 0; tt < GN_TSTEP; ++tt) {
+        const int t = t0 + tt;
+        if (t >= T0) break;
+        const long idx = (long)t * 512 + c;
+        const float v = (y[idx] - m) * rstd * g + b;
+        out[idx] = __float2half_rn(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));
+    }
 }
 
 void hubert_conv0_gn_gelu(const float* wav, int n_samples, const float* w, const float* gamma, const float* beta, float* scratch_y,
@@ -114,8 +124,7 @@ void hubert_conv0_gn_gelu(const float* wav, int n_samples, const float* w, const
     CUDA_CHECK(cudaMemsetAsync(scratch_stats, 0, sizeof(double) * 1024, s));
     hubert_conv0_kernel<<<ceil_div(T0, C0_TSTEP), 512, 0, s>>>(wav, n_samples, w, scratch_y, scratch_stats, T0);
     KERNEL_CHECK();
-    const long n = (long)T0 * 512;
-    hubert_gn_gelu_kernel<<<(unsigned)ceil_div_l(n, 256), 256, 0, s>>>(scratch_y, scratch_stats, gamma, beta, out16, T0);
+    hubert_gn_gelu_kernel<<<ceil_div(T0, GN_TSTEP), 512, 0, s>>>(scratch_y, scratch_stats, gamma, beta, out16, T0);
     KERNEL_CHECK();
     count_launch(2);
 }
