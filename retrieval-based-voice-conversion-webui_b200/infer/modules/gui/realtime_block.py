@@ -32,6 +32,22 @@ def _rms_frames(y: np.ndarray, frame_length: int, hop_length: int) -> np.ndarray
     return np.sqrt(np.mean(np.abs(yp[idx]) ** 2, axis=1, keepdims=True)).T.astype(np.float32)
 
 
+def response_gate(indata: np.ndarray, rms_buffer: np.ndarray, zc: int, threhold: float) -> np.ndarray:
+    """gui.py:951-966: zero the zc-segments whose RMS is under the response threshold (host numpy, as in the reference).  ``rms_buffer``
+    (the last 4 zc samples of the previous call) is updated in place; the returned block is 2 zc longer than the input."""
+    indata = np.append(rms_buffer, indata)
+    rms = _rms_frames(indata, 4 * zc, zc)[:, 2:]
+    rms_buffer[:] = indata[-4 * zc:]
+    indata = indata[2 * zc - zc // 2:]
+    db = 20.0 * np.log10(np.maximum(1e-5, rms))                  # librosa.amplitude_to_db(rms, ref=1.0): amin 1e-5, top_db 80
+    db = np.maximum(db, db.max() - 80.0)
+    quiet = db[0] < threhold
+    for i in range(quiet.shape[0]):
+        if quiet[i]:
+            indata[i * zc: (i + 1) * zc] = 0
+    return indata[zc // 2:]
+
+
 class RealtimeBlock:
     def __init__(self, rvc, samplerate: int = 48000, block_time: float = 0.25, crossfade_time: float = 0.05, extra_time: float = 2.5,
                  I_noise_reduce: bool = False, O_noise_reduce: bool = False, rms_mix_rate: float = 1.0, threhold: float = -60.0,
@@ -99,19 +115,7 @@ class RealtimeBlock:
 
     # ------------------------------------------------------------------------------------------------------------------
     def _gate(self, indata: np.ndarray) -> np.ndarray:
-        """gui.py:951-966: zero the zc-segments whose RMS is under the response threshold (host numpy, as in the reference)."""
-        zc = self.zc
-        indata = np.append(self.rms_buffer, indata)
-        rms = _rms_frames(indata, 4 * zc, zc)[:, 2:]
-        self.rms_buffer[:] = indata[-4 * zc:]
-        indata = indata[2 * zc - zc // 2:]
-        db = 20.0 * np.log10(np.maximum(1e-5, rms))                  # librosa.amplitude_to_db(rms, ref=1.0)
-        db = np.maximum(db, db.max() - 80.0)
-        quiet = db[0] < self.threhold
-        for i in range(quiet.shape[0]):
-            if quiet[i]:
-                indata[i * zc: (i + 1) * zc] = 0
-        return indata[zc // 2:]
+        return response_gate(indata, self.rms_buffer, self.zc, self.threhold)
 
     @torch.no_grad()
     def process(self, indata: np.ndarray) -> np.ndarray:

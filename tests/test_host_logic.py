@@ -415,3 +415,48 @@ def test_mel_filterbank_matches_torchaudio_htk_slaney():
     from oracle import rmvpe as ORM
     fb = torchaudio.functional.melscale_fbanks(513, 30.0, 8000.0, 128, 16000, norm="slaney", mel_scale="htk").t().numpy()
     assert np.abs(ORM.mel_filterbank() - fb).max() < 1e-6
+
+
+def test_realtime_host_side_pieces(tmp_path):
+    """CPU-testable parts of the realtime / batch front doors: the response-threshold gate (gui.py:951-966) against the oracle
+    callback's restatement over consecutive blocks, the TorchGate mask-smoothing filter (torchgate.py:72-126), save_audio's two modes
+    (infer/lib/audio.py:29-56)."""
+    from scipy.io import wavfile
+    from infer.lib.audio import save_audio
+    from infer.modules.gui.realtime_block import response_gate
+    from infer.modules.gui.torchgate import TorchGate
+    from oracle import rtrvc as ORT, torchgate as OT
+    zc = 480
+    rng = np.random.default_rng(5)
+
+    class _Stub:                      # OracleCallback.block's gate needs only these fields
+        tgt_sr = 48000
+    orc = ORT.OracleCallback.__new__(ORT.OracleCallback)
+    orc.zc, orc.threhold, orc.rms_buffer = zc, -40.0, np.zeros(4 * zc, dtype="float32")
+    buf = np.zeros(4 * zc, dtype="float32")
+    for b in range(4):
+        x = (rng.standard_normal(7680) * (0.2 if b % 2 else 0.002)).astype(np.float32)
+        x[: 7680 // 3] *= 0.01
+        got = response_gate(x.copy(), buf, zc, -40.0)
+        # the oracle's literal restatement of the same lines
+        ind = np.append(orc.rms_buffer, x)
+        rms = ORT.rms_frames(ind, 4 * zc, zc)[:, 2:]
+        orc.rms_buffer[:] = ind[-4 * zc:]
+        ind = ind[2 * zc - zc // 2:]
+        db = 20.0 * np.log10(np.maximum(1e-5, rms)); db = np.maximum(db, db.max() - 80.0)
+        for i in np.nonzero(db[0] < -40.0)[0]:
+            ind[i * zc: (i + 1) * zc] = 0
+        ref = ind[zc // 2:]
+        assert got.shape == ref.shape == (7680 + 2 * zc,) and np.array_equal(got, ref) and np.array_equal(buf, orc.rms_buffer)
+        assert (got == 0).any() and (bool((got != 0).any()) == bool(b % 2))      # quiet blocks are gated entirely, loud ones only in part
+    for sr, n_fft in ((48000, 1920), (40000, 1600), (16000, 1024)):
+        f = TorchGate(sr=sr, n_fft=n_fft).smoothing_filter[0, 0]
+        assert torch.equal(f, OT.smoothing_filter(sr, n_fft, n_fft // 4)) and abs(float(f.sum()) - 1.0) < 1e-6
+    i16 = (rng.standard_normal(1000) * 8000).astype(np.int16)
+    save_audio(str(tmp_path / "a.wav"), i16, 48000, f32=True)
+    sr, y = wavfile.read(str(tmp_path / "a.wav"))
+    assert sr == 48000 and y.dtype == np.float32 and np.array_equal(y, i16.astype(np.float32))        # int16-range floats, like the reference
+    fl = np.linspace(-0.5, 0.5, 100).astype(np.float32)
+    save_audio(str(tmp_path / "b.wav"), fl, 16000)
+    sr, y = wavfile.read(str(tmp_path / "b.wav"))
+    assert y.dtype == np.int16 and np.array_equal(y, np.multiply(fl, 32767).astype(np.int16))
