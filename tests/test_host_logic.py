@@ -448,7 +448,7 @@ def test_realtime_host_side_pieces(tmp_path):
             ind[i * zc: (i + 1) * zc] = 0
         ref = ind[zc // 2:]
         assert got.shape == ref.shape == (7680 + 2 * zc,) and np.array_equal(got, ref) and np.array_equal(buf, orc.rms_buffer)
-        assert (got == 0).any() and (bool((got != 0).any()) == bool(b % 2))      # quiet blocks are gated entirely, loud ones only in part
+        assert (got == 0).any() and (b % 2 == 0 or (got != 0).any())      # the quiet third of a loud block is gated, the rest kept
     for sr, n_fft in ((48000, 1920), (40000, 1600), (16000, 1024)):
         f = TorchGate(sr=sr, n_fft=n_fft).smoothing_filter[0, 0]
         assert torch.equal(f, OT.smoothing_filter(sr, n_fft, n_fft // 4)) and abs(float(f.sum()) - 1.0) < 1e-6
