@@ -8,6 +8,7 @@ stages between the host DSP run on the B200 without the reference's four host ro
 from __future__ import annotations
 
 import os
+import threading
 import traceback
 import logging
 from pathlib import Path
@@ -22,6 +23,12 @@ from rvc.f0 import Generator
 from rvc_b200 import engine, faiss_io
 
 logger = logging.getLogger(__name__)
+
+# Launch-side work that touches process-wide state is serialised between the conversion lanes of VC.vc_multi (one thread each):
+# torch's CUDA generator (the noise draws inside a captured graph register offset increments with it -- a capture in one thread while
+# another thread replays or draws eagerly raises "Offset increment outside graph capture"), graph capture itself, and the library's
+# grid cap.  Only the host-side ENQUEUE is under the lock (~0.1 ms for a graph replay); the utterances still overlap on the device.
+_LAUNCH_LOCK = threading.RLock()
 
 bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)     # pipeline.py:23
 zi_h = signal.lfilter_zi(bh, ah)                                # filtfilt's edge state, a constant of the filter
@@ -282,35 +289,36 @@ class Pipeline(object):
         if host_ok and os.environ.get("RVCB_GRAPHS", "1") != "0" and (index is None or isinstance(index, engine.Index)):
             key = (int(audio.shape[0]), id(model), id(net_g), int(sid), float(f0_up_key), id(index), float(index_rate), int(if_f0),
                    int(tgt_sr), float(rms_mix_rate), str(version), float(protect), bool(as_int16), int(resample_sr))
-        ent = self._graphs.get(key) if key is not None else None
-        if ent is not None and "graph" not in ent and not ent.get("failed"):
-            # second sighting: capture (arenas and kernels are warm from the first run)
-            try:
-                ent["x"] = torch.empty_like(x)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):       # other vc_multi lanes keep running
-                    ent["out"] = self._dev_body(ent["x"], *args)
-                ent["graph"] = g
-            except Exception:                           # capture is an optimisation only: keep launching eagerly for this key
-                logger.warning("CUDA graph capture failed, staying eager:\n%s", traceback.format_exc())
-                ent.clear()
-                ent["failed"] = True
-                torch.cuda.synchronize()
-        if key is None or ent is None or "graph" not in ent:
-            if key is not None and ent is None:
-                if len(self._graphs) >= 4:
-                    self._graphs.pop(next(iter(self._graphs)))
-                self._graphs[key] = {}
-            out = self._dev_body(x, *args)
-        else:
-            if "refs" not in ent:
-                ent["refs"] = (model, net_g, index, big_npy)     # the graph bakes their device pointers in: keep them alive (and
-                                                                 # their id()s, which are part of the key, unrecyclable)
-            ent["x"].copy_(x, non_blocking=True)
-            ent["graph"].replay()
-            out = ent["out"]
-            times[2] += time() - t0          # launch time only: the replay is asynchronous like the eager path
+        with _LAUNCH_LOCK:
+            ent = self._graphs.get(key) if key is not None else None
+            if ent is not None and "graph" not in ent and not ent.get("failed"):
+                # second sighting: capture (arenas and kernels are warm from the first run)
+                try:
+                    ent["x"] = torch.empty_like(x)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):       # other vc_multi lanes keep running
+                        ent["out"] = self._dev_body(ent["x"], *args)
+                    ent["graph"] = g
+                except Exception:                           # capture is an optimisation only: keep launching eagerly for this key
+                    logger.warning("CUDA graph capture failed, staying eager:\n%s", traceback.format_exc())
+                    ent.clear()
+                    ent["failed"] = True
+                    torch.cuda.synchronize()
+            if key is None or ent is None or "graph" not in ent:
+                if key is not None and ent is None:
+                    if len(self._graphs) >= 4:
+                        self._graphs.pop(next(iter(self._graphs)))
+                    self._graphs[key] = {}
+                out = self._dev_body(x, *args)
+            else:
+                if "refs" not in ent:
+                    ent["refs"] = (model, net_g, index, big_npy)     # the graph bakes their device pointers in: keep them alive (and
+                                                                     # their id()s, which are part of the key, unrecyclable)
+                ent["x"].copy_(x, non_blocking=True)
+                ent["graph"].replay()
+                out = ent["out"]
+                times[2] += time() - t0          # launch time only: the replay is asynchronous like the eager path
         return out
 
     def pipeline(self, model, net_g, sid, audio, times, f0_up_key, f0_method, file_index, index_rate, if_f0, filter_radius, tgt_sr,
@@ -329,6 +337,14 @@ class Pipeline(object):
             out = self._pipeline_single_dev(model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
                                             rms_mix_rate, version, protect, as_int16=as_i16, resample_sr=resample_sr)
             return out.cpu().numpy()
+        with _LAUNCH_LOCK:          # the reference's control flow with eager launches (noise draws): one lane at a time
+            return self._pipeline_host_flow(model, net_g, sid, audio, times, f0_up_key, f0_method, index, big_npy, index_rate, if_f0,
+                                            filter_radius, tgt_sr, resample_sr, rms_mix_rate, version, protect, f0_file)
+
+    def _pipeline_host_flow(self, model, net_g, sid, audio, times, f0_up_key, f0_method, index, big_npy, index_rate, if_f0, filter_radius,
+                            tgt_sr, resample_sr, rms_mix_rate, version, protect, f0_file):
+        """pipeline.py:221-366 with the reference's own control flow (silence-point chunking, f0 files, given f0): host DSP
+        prologue, device compute per chunk, device epilogue."""
         audio = engine.host_filtfilt(bh, ah, zi_h, audio)       # == signal.filtfilt(bh, ah, audio), bit for bit
         audio_pad = np.pad(audio, (self.window // 2, self.window // 2), mode="reflect")
         opt_ts = []
