@@ -121,6 +121,8 @@ class VC:
         finally:
             self.pipeline._want_int16 = False
         out_sr = resample_sr if self.tgt_sr != resample_sr >= 16000 else self.tgt_sr
+        if hasattr(wav, "result"):                # PendingResult (vc_multi lanes): the copy back is still in flight
+            return out_sr, wav, times
         return out_sr, wav.astype(np.int16, copy=False), times
 
     def vc_single(self, sid, input_audio_path, f0_up_key, f0_file, f0_method, file_index, file_index2, index_rate, filter_radius,
@@ -169,12 +171,43 @@ class VC:
             self._lanes.append(lane)
         return self._lanes[i - 1]
 
+    def _submit(self, lane: "VC", stream, sid, path, f0_up_key, f0_method, file_index, index_rate, filter_radius, resample_sr, rms_mix_rate,
+                protect):
+        """First half of ``vc_single`` on ``lane`` / ``stream``: decode, enqueue the whole utterance and its copy back, do NOT wait.
+        Returns ``finish() -> (info, opt)`` (the second half: wait, format the info string)."""
+        try:
+            audio = np.array(load_audio(path, 16000), dtype=np.float32)
+            lane.pipeline._defer_d2h = True
+            try:
+                with torch.cuda.stream(stream):
+                    out_sr, wav, times = lane._convert(sid, audio, int(f0_up_key), None, f0_method, file_index, index_rate, filter_radius,
+                                                       resample_sr, rms_mix_rate, protect)
+            finally:
+                lane.pipeline._defer_d2h = False
+        except Exception as e:
+            logger.warning(traceback.format_exc())
+            msg = str(e)
+            return lambda: (msg, None)
+
+        def finish():
+            try:
+                w = wav.result() if hasattr(wav, "result") else wav
+                used = not isinstance(file_index, str) or os.path.exists(file_index)
+                index_info = "Index: %s." % file_index if used else "Index not used."
+                return ("Success.\n%s\nTime: npy: %.2fs, f0: %.2fs, infer: %.2fs." % (index_info, *times),
+                        (out_sr, w.astype(np.int16, copy=False)))
+            except Exception as e:
+                logger.warning(traceback.format_exc())
+                return str(e), None
+        return finish
+
     def vc_multi(self, sid, dir_path, opt_root, paths, f0_up_key, f0_method, file_index, file_index2, index_rate, filter_radius,
                  resample_sr, rms_mix_rate, protect, format1) -> Iterator[str]:
-        """modules.py:201-266.  The reference converts the files one after the other; one utterance is latency-bound on a B200 (two
-        front branches of ~130 small launches each, then the synthesizer), so RVCB_LANES (default 2) utterances are kept in flight
-        on one GPU, each on its own lane (thread + streams + handles); results are identical to the serial loop and the log lines
-        come out in the input order.  Under torchrun the list is additionally strided over ranks (one process per GPU)."""
+        """modules.py:201-266.  The reference converts the files one after the other.  With RVCB_LANES > 1 (default 1 = the serial
+        loop) this host thread keeps that many utterances in flight on the GPU: file i is enqueued on lane i mod L (own handle set,
+        stream and captured graph) and collected, in input order, just before its lane is needed again -- no host threads, so nothing
+        contends for the GIL and the noise draws stay single-threaded.  Results equal the serial loop's; the log lines keep the input
+        order.  Under torchrun the list is additionally strided over ranks (one process per GPU)."""
         try:
             dir_path, opt_root = _unquote(dir_path), _unquote(opt_root)
             os.makedirs(opt_root, exist_ok=True)
@@ -182,58 +215,51 @@ class VC:
             # under torchrun the list is strided over ranks exactly like extract_feature_print.py:110
             rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
             todo = todo[rank::world]
-            n_lanes = max(1, min(int(os.environ.get("RVCB_LANES", "2")), len(todo)))
+            n_lanes = max(1, min(int(os.environ.get("RVCB_LANES", "1")), len(todo)))
+            log: List[str] = []
 
-            index_clones: Dict[int, Any] = {}
-
-            def convert(lane_id: int, path: str) -> str:
-                lane = self._lane(lane_id)
-                fi = file_index
-                if lane_id > 0 and hasattr(file_index, "clone") and not isinstance(file_index, str):
-                    if lane_id not in index_clones:                  # a device-resident Index object: one handle per lane
-                        index_clones[lane_id] = file_index.clone()
-                    fi = index_clones[lane_id]
-                info, opt = lane.vc_single(sid, path, f0_up_key, None, f0_method, fi, file_index2, index_rate, filter_radius,
-                                           resample_sr, rms_mix_rate, protect)
+            def record(path: str, info: str, opt) -> str:
                 if "Success" in info:
                     try:
                         out_sr, wav = opt
                         save_audio("%s/%s.%s" % (opt_root, os.path.basename(path), format1), wav, out_sr, f32=True)
                     except Exception:
                         info += traceback.format_exc()
-                return "%s->%s" % (os.path.basename(path), info)
+                log.append("%s->%s" % (os.path.basename(path), info))
+                return "\n".join(log)
 
-            log: List[str] = []
             if n_lanes == 1 or self.net_g is None:
                 for path in todo:
-                    log.append(convert(0, path))
-                    yield "\n".join(log)
+                    info, opt = self.vc_single(sid, path, f0_up_key, None, f0_method, file_index, file_index2, index_rate, filter_radius,
+                                               resample_sr, rms_mix_rate, protect)
+                    yield record(path, info, opt)
             else:
-                import queue
-                from concurrent.futures import ThreadPoolExecutor
-                # the first file goes through lane 0 alone: one-time kernel attribute setup and arena sizing happen single-threaded
-                log.append(convert(0, todo[0]))
-                yield "\n".join(log)
-                for i in range(1, n_lanes):
-                    self._lane(i)
-                free: "queue.Queue[int]" = queue.Queue()
-                for i in range(n_lanes):
-                    free.put(i)
+                # the first file goes through lane 0 alone and synchronously: one-time kernel attribute setup and arena sizing
+                info, opt = self.vc_single(sid, todo[0], f0_up_key, None, f0_method, file_index, file_index2, index_rate, filter_radius,
+                                           resample_sr, rms_mix_rate, protect)
+                yield record(todo[0], info, opt)
                 device = torch.device(self.config.device if "cuda" in str(self.config.device) else "cuda:0")
+                picked = self._pick_index(file_index, file_index2)
+                lanes = [self._lane(i) for i in range(n_lanes)]
                 streams = [torch.cuda.Stream(device=device) for _ in range(n_lanes)]
-
-                def work(path: str) -> str:
-                    lane_id = free.get()
-                    try:
-                        with torch.cuda.device(device), torch.cuda.stream(streams[lane_id]):
-                            return convert(lane_id, path)
-                    finally:
-                        free.put(lane_id)
-
-                with ThreadPoolExecutor(max_workers=n_lanes, thread_name_prefix="vc_lane") as pool:
-                    for line in pool.map(work, todo[1:]):       # results in input order
-                        log.append(line)
-                        yield "\n".join(log)
+                # a device-resident Index object is one handle (one search workspace): every further lane gets its own
+                indexes = [picked if (i == 0 or isinstance(picked, str) or not hasattr(picked, "clone")) else picked.clone()
+                           for i in range(n_lanes)]
+                pending: List[Optional[tuple]] = [None] * n_lanes
+                for i, path in enumerate(todo[1:]):
+                    k = i % n_lanes
+                    if pending[k] is not None:                      # the oldest utterance in flight: collect it, its lane is free again
+                        p_path, p_finish = pending[k]
+                        yield record(p_path, *p_finish())
+                    pending[k] = (path, self._submit(lanes[k], streams[k], sid, path, f0_up_key, f0_method, indexes[k], index_rate,
+                                                     filter_radius, resample_sr, rms_mix_rate, protect))
+                n_sub = len(todo) - 1
+                for j in range(n_lanes):                            # drain in submission order
+                    k = (n_sub + j) % n_lanes
+                    if pending[k] is not None:
+                        p_path, p_finish = pending[k]
+                        pending[k] = None
+                        yield record(p_path, *p_finish())
             yield "\n".join(log)
         except Exception:
             yield traceback.format_exc()

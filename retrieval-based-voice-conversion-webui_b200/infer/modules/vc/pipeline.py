@@ -60,6 +60,25 @@ def change_rms(data1, sr1, data2, sr2, rate):     # pipeline.py:26-45
     return data2
 
 
+class PendingResult:
+    """A device-resident result whose device-to-host copy (into pinned memory, on the stream that produced it) has been queued but not
+    waited for: ``result()`` waits and returns the numpy array.  Lets one host thread keep several utterances in flight."""
+
+    def __init__(self, pipe: "Pipeline", dev: torch.Tensor):
+        n = dev.numel()
+        buf = pipe._out_pinned.get(dev.dtype)
+        if buf is None or buf.numel() < n:
+            buf = pipe._out_pinned[dev.dtype] = torch.empty(max(n, 1 << 19), dtype=dev.dtype, pin_memory=True)
+        self._host = buf[:n]
+        self._host.copy_(dev.reshape(-1), non_blocking=True)
+        self._ev = torch.cuda.Event()
+        self._ev.record(torch.cuda.current_stream())
+
+    def result(self) -> np.ndarray:
+        self._ev.synchronize()
+        return self._host.numpy().copy()          # the pinned buffer is reused by this lane's next utterance
+
+
 class Pipeline(object):
     def __init__(self, tgt_sr, config):
         self.x_pad, self.x_query, self.x_center, self.x_max, self.is_half = (
@@ -78,6 +97,8 @@ class Pipeline(object):
         self._index_cache = {}
         self._side = torch.cuda.Stream(device=self.device)
         self._resamplers = {}          # (tgt_sr, resample_sr) -> device sinc table of the resample_sr branch
+        self._out_pinned = {}          # dtype -> pinned result buffer of PendingResult (one utterance in flight per Pipeline)
+        self._defer_d2h = False
         # RMVPE ends in the serial BiGRU and is the longer front branch: it gets a high-priority stream so that its CTAs are placed
         # first whenever SMs free up, and HuBERT + retrieval fill the rest (RVCB_F0_PRIO=0: RMVPE stays on the caller's stream)
         self._f0_stream = torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("RVCB_F0_PRIO", "1") != "0" else None
@@ -336,6 +357,8 @@ class Pipeline(object):
             as_i16 = getattr(self, "_want_int16", False)
             out = self._pipeline_single_dev(model, net_g, sid, audio, times, f0_up_key, index, big_npy, index_rate, if_f0, tgt_sr,
                                             rms_mix_rate, version, protect, as_int16=as_i16, resample_sr=resample_sr)
+            if getattr(self, "_defer_d2h", False):
+                return PendingResult(self, out)          # VC.vc_multi: the copy back is queued, the caller collects it later
             return out.cpu().numpy()
         with _LAUNCH_LOCK:          # the reference's control flow with eager launches (noise draws): one lane at a time
             return self._pipeline_host_flow(model, net_g, sid, audio, times, f0_up_key, f0_method, index, big_npy, index_rate, if_f0,
