@@ -41,6 +41,7 @@ class VC:
         self.n_spk = self.tgt_sr = self.version = self.if_f0 = None
         self._loaded_sid = None
         self._lanes: List["VC"] = []          # extra conversion lanes of vc_multi (own handles / streams / graphs each)
+        self._index_clones: Dict[tuple, tuple] = {}     # (id(index object), lane) -> (index object, its per-lane clone)
 
     # ------------------------------------------------------------------ model selection (modules.py:32-117)
     def _protect_updates(self, extra: tuple) -> Tuple[Dict[str, Any], Dict[str, Any]]:
@@ -61,6 +62,7 @@ class VC:
         """Build the synthesizer container and the pipeline for ``sid`` (a file under $weight_root, or the dict a .pth holds)."""
         self._loaded_sid = sid
         self._lanes.clear()
+        self._index_clones.clear()
         if isinstance(sid, dict):
             self.net_g, self.cpt = get_synthesizer(sid, self.config.device)
             name = sid.get("name", "in-memory")
@@ -171,6 +173,15 @@ class VC:
             self._lanes.append(lane)
         return self._lanes[i - 1]
 
+    def _index_clone(self, index, lane_id: int):
+        """Per-lane handle of a device-resident Index object, created once (the captured graphs are keyed by the handle's identity)."""
+        key = (id(index), lane_id)
+        if key not in self._index_clones:
+            if len(self._index_clones) >= 8:
+                self._index_clones.clear()
+            self._index_clones[key] = (index, index.clone())          # the original is kept alive so its id() cannot be recycled
+        return self._index_clones[key][1]
+
     def _submit(self, lane: "VC", stream, sid, path, f0_up_key, f0_method, file_index, index_rate, filter_radius, resample_sr, rms_mix_rate,
                 protect):
         """First half of ``vc_single`` on ``lane`` / ``stream``: decode, enqueue the whole utterance and its copy back, do NOT wait.
@@ -204,7 +215,7 @@ class VC:
     def vc_multi(self, sid, dir_path, opt_root, paths, f0_up_key, f0_method, file_index, file_index2, index_rate, filter_radius,
                  resample_sr, rms_mix_rate, protect, format1) -> Iterator[str]:
         """modules.py:201-266.  The reference converts the files one after the other.  With RVCB_LANES > 1 (default 1 = the serial
-        loop) this host thread keeps that many utterances in flight on the GPU: file i is enqueued on lane i mod L (own handle set,
+        loop; opt-in) this host thread keeps that many utterances in flight on the GPU: file i is enqueued on lane i mod L (own handle set,
         stream and captured graph) and collected, in input order, just before its lane is needed again -- no host threads, so nothing
         contends for the GIL and the noise draws stay single-threaded.  Results equal the serial loop's; the log lines keep the input
         order.  Under torchrun the list is additionally strided over ranks (one process per GPU)."""
@@ -243,7 +254,7 @@ class VC:
                 lanes = [self._lane(i) for i in range(n_lanes)]
                 streams = [torch.cuda.Stream(device=device) for _ in range(n_lanes)]
                 # a device-resident Index object is one handle (one search workspace): every further lane gets its own
-                indexes = [picked if (i == 0 or isinstance(picked, str) or not hasattr(picked, "clone")) else picked.clone()
+                indexes = [picked if (i == 0 or isinstance(picked, str) or not hasattr(picked, "clone")) else self._index_clone(picked, i)
                            for i in range(n_lanes)]
                 pending: List[Optional[tuple]] = [None] * n_lanes
                 for i, path in enumerate(todo[1:]):
