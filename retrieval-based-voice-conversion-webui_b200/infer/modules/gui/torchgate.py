@@ -1,8 +1,8 @@
 """Drop-in for the reference's realtime spectral gate (infer/modules/gui/torchgate.py: TorchGate) on the B200 library: same
 constructor arguments, ``forward(x, xn=None)`` with x [B, L] / xn [B, Ln] device tensors -> [B, hop * (L // hop)], ``.to(device)``.
 The STFT, the dB statistics, the mask, its smoothing, the inverse STFT and the overlap-add are CUDA kernels behind
-``rvcb_torchgate_apply`` (csrc/torchgate.cu); this file only derives the smoothing filter (torchgate.py:72-126, a handful of
-floats) and owns the handle.  There is no CPU path: without the CUDA library the constructor raises."""
+``rvcb_torchgate_apply`` (csrc/torchgate.cu); this file derives the mask-smoothing filter (torchgate.py:72-126, a handful of
+floats) and owns the handle.  There is no CPU path: the first call creates the CUDA handle or raises."""
 from __future__ import annotations
 
 from typing import Optional
@@ -12,8 +12,27 @@ import torch
 from rvc_b200 import engine
 
 
-def _linspace(start, stop, num, endpoint=True):
-    return torch.linspace(start, stop, num) if endpoint else torch.linspace(start, stop, num + 1)[:-1]      # gui/utils.py:43-70
+def _ramp(n: int) -> torch.Tensor:
+    """n rising steps k / (n + 1), the peak 1, n falling steps: 2 n + 1 values, the same torch.linspace calls as the reference."""
+    return torch.cat([torch.linspace(0, 1, n + 2)[1:-1], torch.linspace(1, 0, n + 2)[:-1]])
+
+
+def mask_smoothing_filter(sr: int, n_fft: int, hop: int, freq_hz: Optional[float], time_ms: Optional[float]) -> Optional[torch.Tensor]:
+    """[2 nf + 1, 2 nt + 1] outer product of two triangles normalised to sum 1 (rows = frequency), or None when there is nothing to
+    smooth; nf / nt = the smoothing widths in bins / frames, truncated like the reference does."""
+    if freq_hz is None and time_ms is None:
+        return None
+    bin_hz, frame_ms = sr / (n_fft / 2), (hop / sr) * 1000
+    nf = 1 if freq_hz is None else int(freq_hz / bin_hz)
+    nt = 1 if time_ms is None else int(time_ms / frame_ms)
+    if nf < 1:
+        raise ValueError(f"freq_mask_smooth_hz needs to be at least {int(bin_hz)} Hz")
+    if nt < 1:
+        raise ValueError(f"time_mask_smooth_ms needs to be at least {int(frame_ms)} ms")
+    if nf == 1 and nt == 1:
+        return None
+    f = torch.outer(_ramp(nf), _ramp(nt))
+    return f / f.sum()
 
 
 class TorchGate:
@@ -21,37 +40,20 @@ class TorchGate:
                  temp_coeff_nonstationary: float = 0.1, n_movemean_nonstationary: int = 20, prop_decrease: float = 1.0, n_fft: int = 1024,
                  win_length: Optional[int] = None, hop_length: Optional[int] = None, freq_mask_smooth_hz: Optional[float] = 500,
                  time_mask_smooth_ms: Optional[float] = 50):
-        assert 0.0 <= prop_decrease <= 1.0
-        self.sr, self.nonstationary, self.prop_decrease = sr, nonstationary, prop_decrease
-        self.n_fft = n_fft
-        self.win_length = n_fft if win_length is None else win_length
-        if self.win_length != n_fft:
+        if not 0.0 <= prop_decrease <= 1.0:
+            raise AssertionError("prop_decrease must be in [0, 1]")
+        if win_length not in (None, n_fft):
             raise NotImplementedError("win_length != n_fft (the reference never passes it: gui.py:869-871)")
-        self.hop_length = self.win_length // 4 if hop_length is None else hop_length
+        self.sr, self.n_fft, self.win_length = sr, n_fft, n_fft
+        self.hop_length = n_fft // 4 if hop_length is None else hop_length
+        self.nonstationary, self.prop_decrease = nonstationary, prop_decrease
         self.n_std_thresh_stationary = n_std_thresh_stationary
-        self.temp_coeff_nonstationary = temp_coeff_nonstationary
+        self.n_thresh_nonstationary, self.temp_coeff_nonstationary = n_thresh_nonstationary, temp_coeff_nonstationary
         self.n_movemean_nonstationary = n_movemean_nonstationary
-        self.n_thresh_nonstationary = n_thresh_nonstationary
         self.freq_mask_smooth_hz, self.time_mask_smooth_ms = freq_mask_smooth_hz, time_mask_smooth_ms
-        self.smoothing_filter = self._generate_mask_smoothing_filter()
-        self._h = None
-        self._device_index = 0
-
-    def _generate_mask_smoothing_filter(self):
-        if self.freq_mask_smooth_hz is None and self.time_mask_smooth_ms is None:
-            return None
-        n_grad_freq = 1 if self.freq_mask_smooth_hz is None else int(self.freq_mask_smooth_hz / (self.sr / (self.n_fft / 2)))
-        if n_grad_freq < 1:
-            raise ValueError(f"freq_mask_smooth_hz needs to be at least {int((self.sr / (self.n_fft / 2)))} Hz")
-        n_grad_time = 1 if self.time_mask_smooth_ms is None else int(self.time_mask_smooth_ms / ((self.hop_length / self.sr) * 1000))
-        if n_grad_time < 1:
-            raise ValueError(f"time_mask_smooth_ms needs to be at least {int((self.hop_length / self.sr) * 1000)} ms")
-        if n_grad_time == 1 and n_grad_freq == 1:
-            return None
-        v_f = torch.cat([_linspace(0, 1, n_grad_freq + 1, endpoint=False), _linspace(1, 0, n_grad_freq + 2)])[1:-1]
-        v_t = torch.cat([_linspace(0, 1, n_grad_time + 1, endpoint=False), _linspace(1, 0, n_grad_time + 2)])[1:-1]
-        f = torch.outer(v_f, v_t).unsqueeze(0).unsqueeze(0)
-        return f / f.sum()
+        filt = mask_smoothing_filter(sr, n_fft, self.hop_length, freq_mask_smooth_hz, time_mask_smooth_ms)
+        self.smoothing_filter = None if filt is None else filt[None, None]          # [1, 1, rows, cols] like the reference's buffer
+        self._handle_obj, self._device_index = None, 0
 
     def to(self, device):
         dev = torch.device(device)
@@ -60,13 +62,13 @@ class TorchGate:
         self._device_index = dev.index or 0
         return self
 
-    def _handle(self):
-        if self._h is None:
+    def _handle(self) -> "engine.TorchGateHandle":
+        if self._handle_obj is None:
             filt = None if self.smoothing_filter is None else self.smoothing_filter[0, 0]
-            self._h = engine.TorchGateHandle(self.sr, self.n_fft, self.hop_length, self.nonstationary, self.n_std_thresh_stationary,
-                                             self.n_thresh_nonstationary, self.temp_coeff_nonstationary, self.n_movemean_nonstationary,
-                                             self.prop_decrease, filt, self._device_index)
-        return self._h
+            self._handle_obj = engine.TorchGateHandle(self.sr, self.n_fft, self.hop_length, self.nonstationary, self.n_std_thresh_stationary,
+                                                      self.n_thresh_nonstationary, self.temp_coeff_nonstationary,
+                                                      self.n_movemean_nonstationary, self.prop_decrease, filt, self._device_index)
+        return self._handle_obj
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, xn: Optional[torch.Tensor] = None) -> torch.Tensor:
