@@ -147,7 +147,26 @@ def torchgate():
     np.savez_compressed(os.path.join(OUT, "torchgate.npz"), **out)
 
 
+def phase_vocoder():
+    """The reference's OWN phase_vocoder (gui.py:27-48).  gui.py cannot be imported (FreeSimpleGUI, sounddevice, ...): the function's
+    source is cut out of the file with ast and executed with torch / numpy in scope -- the code that runs is the reference's."""
+    import ast
+    src = open("/root/reference/gui.py").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "phase_vocoder")
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "/root/reference/gui.py", "exec"), ns)
+    ref_pv = ns["phase_vocoder"]
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for n in (1920, 1600, 441):                                   # even (48 k / 40 k) and odd (44.1 k: zc = 441) frame lengths
+        fade_in = torch.sin(0.5 * np.pi * torch.linspace(0.0, 1.0, steps=n, dtype=torch.float32)) ** 2
+        fade_out = 1 - fade_in
+        a, b = torch.randn(n, generator=g) * 0.2, torch.randn(n, generator=g) * 0.2
+        out[f"a{n}"], out[f"b{n}"], out[f"y{n}"] = a.numpy(), b.numpy(), ref_pv(a, b, fade_out, fade_in).numpy()
+    np.savez_compressed(os.path.join(OUT, "phase_vocoder.npz"), **out)
+
+
 if __name__ == "__main__":
-    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate()
+    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -125,3 +125,14 @@ def test_resample_table_equals_torchaudio():
         k, w, up, down = engine.sinc_resample_kernel(o, n)
         r = tat.Resample(o, n, dtype=torch.float32)
         assert torch.equal(k, r.kernel[:, 0]) and w == r.width and (up, down) == (n // math.gcd(o, n), o // math.gcd(o, n))
+
+
+def test_phase_vocoder_oracle_matches_reference_golden():
+    """oracle.rtrvc.phase_vocoder vs the outputs of the reference's own function (gui.py:27-48, executed from its source by
+    tests/golden/make_golden.py): same torch ops in the same order -> bit-equal."""
+    from oracle import rtrvc as ORT
+    z = np.load(os.path.join(G, "phase_vocoder.npz"))
+    for n in (1920, 1600, 441):
+        fi, fo = ORT.fade_windows(n)
+        y = ORT.phase_vocoder(torch.from_numpy(z[f"a{n}"]), torch.from_numpy(z[f"b{n}"]), fo, fi).numpy()
+        assert np.array_equal(y, z[f"y{n}"]), n
