@@ -1,6 +1,9 @@
 """Oracle: the realtime engine ``infer.lib.rtrvc.RVC.infer`` and the per-block tail of gui.py's audio callback, fp32 CPU.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned where the reference can be executed here: ``phase_vocoder``, the SOLA step and the
+callback's input side (rings, TorchGate, cross-fade, resampling) are bit-equal to the reference's own statements run from its source
+(tests/golden/make_golden.py: phase_vocoder(), callback_pieces(); tests/test_oracle_golden.py).  ``RVC.infer`` (fairseq, faiss) and the
+envelope mix (librosa) are restatements.
 
 Reference sites restated:
   RVC.__init__ state (pitch ring of 1024 frames)       infer/lib/rtrvc.py:63-66

@@ -166,7 +166,90 @@ def phase_vocoder():
     np.savez_compressed(os.path.join(OUT, "phase_vocoder.npz"), **out)
 
 
+def callback_geometry(sr=24000, block_time=0.16, crossfade_time=0.05, extra_time=0.5):
+    """gui.py:783-815 for a small configuration (24 kHz device rate: zc = 240, 3:2 resampler to 16 kHz)."""
+    zc = sr // 100
+    block = int(np.round(block_time * sr / zc)) * zc
+    cross = int(np.round(crossfade_time * sr / zc)) * zc
+    extra = int(np.round(extra_time * sr / zc)) * zc
+    return dict(sr=sr, zc=zc, block_frame=block, block_frame_16k=160 * block // zc, crossfade_frame=cross,
+                sola_buffer_frame=min(cross, 4 * zc), sola_search_frame=zc, extra_frame=extra)
+
+
+def callback_pieces():
+    """Statements of the reference's OWN realtime callback (gui.py GUI.audio_infer), cut out of the file with ast and executed on a
+    stand-in ``self``: (a) the input rings + input noise gate + cross-fade + resampling to 16 kHz (gui.py:964-999), with the
+    reference's own TorchGate and torchaudio's Resample as ``self.tg`` / ``self.resampler``; (b) the SOLA step (gui.py:1058-1090),
+    sin^2 and phase-vocoder cross-fades.  Inputs come from seeds; only the per-block outputs are stored."""
+    import ast
+    import sys as _sys
+    import types
+    import torch.nn.functional as F_
+    import torchaudio.transforms as tat
+    tree = ast.parse(open("/root/reference/gui.py").read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "audio_infer")
+    pv = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "phase_vocoder")
+    first = next(i for i, st in enumerate(fn.body) if isinstance(st, ast.Assign) and "self.input_wav[:-self.block_frame]" in ast.unparse(st))
+    gate_if = next(i for i, st in enumerate(fn.body) if isinstance(st, ast.If) and "I_noise_reduce" in ast.unparse(st.test))
+    sola0 = next(i for i, st in enumerate(fn.body) if isinstance(st, ast.Assign) and ast.unparse(st).startswith("conv_input"))
+    sola1 = next(i for i, st in enumerate(fn.body) if isinstance(st, ast.Assign) and ast.unparse(st).startswith("self.sola_buffer[:]"))
+
+    def make(name, args, stmts, ret):
+        f = ast.FunctionDef(name=name, args=ast.arguments(posonlyargs=[], args=[ast.arg(arg=a) for a in args], kwonlyargs=[], kw_defaults=[],
+                                                          defaults=[]),
+                            body=list(stmts) + [ast.parse("return " + ret).body[0]], decorator_list=[])
+        return ast.fix_missing_locations(ast.Module(body=[pv, f], type_ignores=[]))
+    ns = {"torch": torch, "np": np, "F": F_, "sys": _sys}
+    exec(compile(make("ref_pre", ["self", "indata"], fn.body[first:gate_if + 1], "None"), "/root/reference/gui.py", "exec"), ns)
+    exec(compile(make("ref_sola", ["self", "infer_wav"], fn.body[sola0:sola1 + 1], "infer_wav, sola_offset"), "/root/reference/gui.py", "exec"), ns)
+    # the reference's TorchGate (same import trick as torchgate())
+    if "librosa" not in sys.modules:
+        lib = types.ModuleType("librosa"); util = types.ModuleType("librosa.util")
+        util.pad_center = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        lib.util = util
+        sys.modules["librosa"] = lib; sys.modules["librosa.util"] = util
+    saved_path, saved_mods = sys.path[:], {k: sys.modules.pop(k) for k in list(sys.modules) if k == "infer" or k.startswith("infer.")}
+    sys.path[:] = ["/root/reference"] + [p for p in sys.path if "webui_b200" not in p]
+    try:
+        from infer.modules.gui.torchgate import TorchGate
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "infer" or k.startswith("infer.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+    geo = callback_geometry()
+    zc, block, sbf = geo["zc"], geo["block_frame"], geo["sola_buffer_frame"]
+    n_in = geo["extra_frame"] + geo["crossfade_frame"] + geo["sola_search_frame"] + block
+    fade_in = torch.sin(0.5 * np.pi * torch.linspace(0.0, 1.0, steps=sbf, dtype=torch.float32)) ** 2
+    out = {}
+    me = types.SimpleNamespace(
+        **{k: geo[k] for k in ("zc", "block_frame", "block_frame_16k", "sola_buffer_frame", "sola_search_frame")},
+        input_wav=torch.zeros(n_in), input_wav_denoise=torch.zeros(n_in), input_wav_res=torch.zeros(160 * n_in // zc),
+        nr_buffer=torch.zeros(sbf), fade_in_window=fade_in, fade_out_window=1 - fade_in,
+        resampler=tat.Resample(orig_freq=geo["sr"], new_freq=16000, dtype=torch.float32),
+        tg=TorchGate(sr=geo["sr"], n_fft=4 * zc, prop_decrease=0.9),
+        gui_config=types.SimpleNamespace(I_noise_reduce=True), config=types.SimpleNamespace(device="cpu"))
+    g = torch.Generator().manual_seed(91)
+    for b in range(3):
+        indata = (torch.randn(block, generator=g) * (0.3 if b != 1 else 0.02)).numpy()
+        ns["ref_pre"](me, indata)
+        out[f"pre_res{b}"] = me.input_wav_res[-geo["block_frame_16k"] - 160:].numpy().copy()
+        out[f"pre_den{b}"] = me.input_wav_denoise[-block:].numpy().copy()
+        out[f"pre_nr{b}"] = me.nr_buffer.numpy().copy()
+    for use_pv in (False, True):
+        me = types.SimpleNamespace(**{k: geo[k] for k in ("block_frame", "sola_buffer_frame", "sola_search_frame")},
+                                   sola_buffer=torch.zeros(sbf), fade_in_window=fade_in, fade_out_window=1 - fade_in,
+                                   gui_config=types.SimpleNamespace(use_pv=use_pv), config=types.SimpleNamespace(device="cpu"))
+        g = torch.Generator().manual_seed(92)
+        for b in range(3):
+            y = torch.randn(block + sbf + geo["sola_search_frame"], generator=g) * 0.2
+            w, off = ns["ref_sola"](me, y.clone())
+            out[f"sola{int(use_pv)}_{b}"] = w[:block].numpy().copy()
+            out[f"sola{int(use_pv)}_off{b}"] = np.int64(int(off))
+    np.savez_compressed(os.path.join(OUT, "callback_pieces.npz"), **out)
+
+
 if __name__ == "__main__":
-    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder()
+    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -136,3 +136,37 @@ def test_phase_vocoder_oracle_matches_reference_golden():
         fi, fo = ORT.fade_windows(n)
         y = ORT.phase_vocoder(torch.from_numpy(z[f"a{n}"]), torch.from_numpy(z[f"b{n}"]), fo, fi).numpy()
         assert np.array_equal(y, z[f"y{n}"]), n
+
+
+def test_callback_oracle_matches_the_reference_statements():
+    """oracle.rtrvc.OracleCallback / SolaTail vs outputs of the reference's OWN callback statements (gui.py GUI.audio_infer: the input
+    rings + input noise gate + cross-fade + 16 kHz resampling, and the SOLA step with both cross-fades), executed from the reference's
+    source by tests/golden/make_golden.py::callback_pieces on a stand-in ``self``.  Inputs are re-drawn from the same seeds."""
+    from oracle import rtrvc as ORT
+    z = np.load(os.path.join(G, "callback_pieces.npz"))
+    sr, zc = 24000, 240
+
+    class _Silent:                                    # OracleCallback needs an engine: the pre-processing under test runs before it
+        tgt_sr = sr
+
+        def infer(self, wav, block_frame_16k, skip_head, return_length):
+            return np.zeros(return_length * zc, dtype=np.float32)
+    orc = ORT.OracleCallback(_Silent(), samplerate=sr, block_time=0.16, crossfade_time=0.05, extra_time=0.5, I_noise_reduce=True)
+    assert (orc.block_frame, orc.block_frame_16k, orc.sola_buffer_frame) == (3840, 2560, 960)
+    g = torch.Generator().manual_seed(91)
+    for b in range(3):
+        indata = (torch.randn(orc.block_frame, generator=g) * (0.3 if b != 1 else 0.02)).numpy()
+        orc.block(indata)
+        assert np.array_equal(orc.input_wav_res[-orc.block_frame_16k - 160:].numpy(), z[f"pre_res{b}"]), b
+        assert np.array_equal(orc.input_wav_denoise[-orc.block_frame:].numpy(), z[f"pre_den{b}"]), b
+        assert np.array_equal(orc.nr_buffer.numpy(), z[f"pre_nr{b}"]), b
+    for use_pv in (False, True):
+        tail = ORT.SolaTail(3840, 960, 240, use_pv=use_pv)
+        g = torch.Generator().manual_seed(92)
+        offs = []
+        for b in range(3):
+            y = torch.randn(3840 + 960 + 240, generator=g) * 0.2
+            out, off = tail.step(y)
+            offs.append(off)
+            assert off == int(z[f"sola{int(use_pv)}_off{b}"]) and np.array_equal(out.numpy(), z[f"sola{int(use_pv)}_{b}"]), (use_pv, b)
+        assert len(set(offs)) > 1
