@@ -11,6 +11,10 @@ Reference sites restated:
   Pipeline.pipeline                 infer/modules/vc/pipeline.py:186-366
 Noise for the synthesizer is drawn from an explicit ``torch.Generator`` so the
 product can be fed the very same tensors.
+
+Pinned: ``vc`` and ``pipeline`` are bit-equal to the reference's own methods executed from their source on duck-typed components
+(tests/golden/make_golden.py: vc_glue(), pipeline_flow(); tests/test_oracle_golden.py) -- except the faiss / librosa branches, which
+cannot run in the build container.
 """
 from __future__ import annotations
 

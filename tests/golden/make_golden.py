@@ -249,7 +249,97 @@ def callback_pieces():
     np.savez_compressed(os.path.join(OUT, "callback_pieces.npz"), **out)
 
 
+def vc_glue():
+    """The reference's OWN ``Pipeline.vc`` (infer/modules/vc/pipeline.py:76-184), cut out of the file with ast (the module itself needs
+    faiss / librosa to import) and executed with duck-typed components: ``model`` = the oracle HuBERT (so only the glue is under test),
+    ``index`` = the oracle IVF-Flat object, ``net_g`` = a recorder that keeps what reaches the synthesizer.  Pins the glue arithmetic of
+    rows a3 / a6: retrieval weights and blend, x2 nearest up-sampling, p_len truncation, protect mix, final_proj for v1."""
+    import ast
+    import types
+    from time import time as _time
+    import torch.nn.functional as F_
+    from oracle import hubert as OH, ivf as OI
+    tree = ast.parse(open("/root/reference/infer/modules/vc/pipeline.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Pipeline")
+    vc = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "vc")
+    ns = {"torch": torch, "np": np, "F": F_, "time": _time}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[vc], type_ignores=[])), "/root/reference/infer/modules/vc/pipeline.py", "exec"), ns)
+    ref_vc = ns["vc"]
+    hw = OW.hubert_weights(777)
+
+    class Model:
+        def extract_features(self, source, padding_mask, output_layer):
+            assert not bool(padding_mask.any())
+            return (OH.extract_features(hw, source.float(), output_layer),)
+
+        def final_proj(self, x):
+            return OH.final_proj(hw, x)
+
+    class Recorder:
+        def infer(self, feats, p_len, sid, pitch=None, pitchf=None):
+            self.seen = (feats.clone(), int(p_len[0]), None if pitch is None else pitch.clone(), None if pitchf is None else pitchf.clone())
+            return torch.zeros(1, 1, 8)
+    me = types.SimpleNamespace(is_half=False, device="cpu", window=160)
+    audio0 = OW.synth_voice(0.62, seed=12).numpy().astype(np.float32)            # 9920 samples: 30 HuBERT frames -> 60, p_len 62 -> 60
+    idx = OI.build_ivf(OW.index_vectors(500, 768, 3).numpy(), 8, seed=0, exact_assign=True)
+    big = idx.reconstruct_n(0, idx.ntotal)
+    p_len = audio0.shape[0] // 160
+    pitchf = torch.zeros(1, p_len); pitchf[0, 10:40] = 180.0 + torch.arange(30)
+    pitch = torch.where(pitchf > 0, torch.full_like(pitchf, 60), torch.ones_like(pitchf)).long()
+    out = {}
+    rec = Recorder()
+    ref_vc(me, Model(), rec, torch.tensor([0]), audio0, pitch, pitchf, [0, 0, 0], idx, big, 0.75, "v2", 0.33)
+    out["v2_phone"], out["v2_plen"] = rec.seen[0][0, :, ::32].numpy(), np.int64(rec.seen[1])
+    out["v2_pitchf"] = rec.seen[3].numpy()
+    rec = Recorder()
+    ref_vc(me, Model(), rec, torch.tensor([0]), audio0, pitch, pitchf, [0, 0, 0], None, None, 0.0, "v1", 0.5)
+    out["v1_phone"], out["v1_plen"] = rec.seen[0][0, :, ::16].numpy(), np.int64(rec.seen[1])
+    np.savez_compressed(os.path.join(OUT, "vc_glue.npz"), **out)
+
+
+def chunk_stub_vc(audio0, pitch, pitchf, window=160, upp=16):
+    """Deterministic stand-in for ``vc`` shared by this generator and the test: one output frame of ``upp`` samples per input frame,
+    built from that frame's samples and its pitch values, so any mis-sliced chunk / pitch window / trim shows up in the output."""
+    n = audio0.shape[0] // window
+    fr = np.asarray(audio0[: n * window], dtype=np.float32).astype(np.float64).reshape(n, window)      # vc casts to float32 first (pipeline.py:91-95)
+    v = fr.mean(1) + 0.25 * np.abs(fr).max(1)
+    if pitchf is not None:
+        m = min(n, pitchf.shape[1])
+        v[:m] += 1e-3 * pitchf[0, :m].double().numpy() + 1e-4 * pitch[0, :m].double().numpy()
+    return np.repeat(v, upp).astype(np.float32) * np.tile(np.linspace(0.5, 1.0, upp, dtype=np.float32), n)
+
+
+def pipeline_flow():
+    """The reference's OWN ``Pipeline.pipeline`` (pipeline.py:186-366), cut out with ast and run on a stand-in ``self`` whose ``vc`` is
+    chunk_stub_vc: silence-point search, per-chunk audio / pitch windows, x_pad trimming, concatenation, peak scaling -- a 10.3 s input
+    with x_max = 4 s gives three cut points.  (No index file, resample_sr = 0, rms_mix_rate = 1: those branches need faiss / librosa.)"""
+    import ast
+    import types
+    from time import time as _time
+    from scipy import signal
+    tree = ast.parse(open("/root/reference/infer/modules/vc/pipeline.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Pipeline")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "pipeline")
+    bh, ah = signal.butter(N=5, Wn=48, btype="high", fs=16000)                 # pipeline.py:23
+    ns = {"torch": torch, "np": np, "os": os, "signal": signal, "time": _time, "bh": bh, "ah": ah,
+          "traceback": __import__("traceback")}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[])), "/root/reference/infer/modules/vc/pipeline.py", "exec"), ns)
+    sr, tgt_sr, x_pad, x_query, x_center, x_max = 16000, 1600, 1, 1, 3, 4
+    me = types.SimpleNamespace(window=160, sr=sr, device="cpu", t_pad=sr * x_pad, t_pad_tgt=tgt_sr * x_pad, t_pad2=sr * x_pad * 2,
+                               t_query=sr * x_query, t_center=sr * x_center, t_max=sr * x_max)
+    me.vc = lambda model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect: chunk_stub_vc(audio0, pitch, pitchf)
+    audio = OW.synth_voice(10.3, seed=14).numpy().astype(np.float32)
+    audio[40000:52000] *= 0.01; audio[90000:100000] *= 0.02                   # quiet stretches for the cut-point search
+    p_len = (audio.shape[0] + 2 * me.t_pad) // 160
+    pitchf = (100.0 + np.arange(p_len) * 0.37).astype(np.float64)
+    pitch = (1 + np.arange(p_len) % 250).astype(np.int64)
+    out = ns["pipeline"](me, None, None, 0, audio.copy(), [0, 0, 0], 0, (pitch, pitchf), "", 0.0, 2, 3, tgt_sr, 0, 1.0, "v2", 0.33)
+    out0 = ns["pipeline"](me, None, None, 0, audio.copy(), [0, 0, 0], 0, "rmvpe", "", 0.0, 0, 3, tgt_sr, 0, 1.0, "v2", 0.33)   # no-f0 model
+    np.savez_compressed(os.path.join(OUT, "pipeline_flow.npz"), out=out[::3].astype(np.float32), n=np.int64(out.shape[0]),
+                        total=np.float64(np.abs(out.astype(np.float64)).sum()), out_nof0=out0[::3].astype(np.float32), n_nof0=np.int64(out0.shape[0]))
+
+
 if __name__ == "__main__":
-    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces()
+    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces(); vc_glue(); pipeline_flow()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

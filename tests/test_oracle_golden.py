@@ -170,3 +170,64 @@ def test_callback_oracle_matches_the_reference_statements():
             offs.append(off)
             assert off == int(z[f"sola{int(use_pv)}_off{b}"]) and np.array_equal(out.numpy(), z[f"sola{int(use_pv)}_{b}"]), (use_pv, b)
         assert len(set(offs)) > 1
+
+
+def test_pipeline_vc_glue_oracle_matches_the_reference_method():
+    """oracle.pipeline.OraclePipeline.vc vs what the reference's OWN ``Pipeline.vc`` (pipeline.py:76-184, executed from its source on
+    duck-typed components by tests/golden/make_golden.py::vc_glue) hands to the synthesizer: retrieval weights + blend, x2 nearest
+    up-sampling, p_len truncation, protect mix, final_proj (v1) -- bit-equal on the stored channel subset."""
+    from oracle import ivf as OI, pipeline as OP, weights as OW
+    z = np.load(os.path.join(G, "vc_glue.npz"))
+    hw = OW.hubert_weights(777)
+    audio0 = OW.synth_voice(0.62, seed=12).numpy().astype(np.float32)
+    idx = OI.build_ivf(OW.index_vectors(500, 768, 3).numpy(), 8, seed=0, exact_assign=True)
+    big = idx.reconstruct_n(0, idx.ntotal)
+    p_len = audio0.shape[0] // 160
+    pitchf = torch.zeros(1, p_len); pitchf[0, 10:40] = 180.0 + torch.arange(30)
+    pitch = torch.where(pitchf > 0, torch.full_like(pitchf, 60), torch.ones_like(pitchf)).long()
+    seen = {}
+    real_synth = OP.OS.synth_infer
+    try:
+        OP.OS.synth_infer = lambda w, cfg, feats, lens, sid, p, pf, n1, n2, **kw: (seen.update(phone=feats.clone(), plen=int(lens[0]), pf=pf) or
+                                                                                   torch.zeros(1, 1, 8))
+        op = OP.OraclePipeline(48000, 1, 6, 38, 41, hw, None, None, OW.V2_48K_CONFIG, noise_seed=0)
+        op.vc(torch.tensor([0]), audio0, pitch, pitchf, idx, big, 0.75, "v2", 0.33)
+        assert seen["plen"] == int(z["v2_plen"]) == 60 and np.array_equal(seen["phone"][0, :, ::32].numpy(), z["v2_phone"])
+        assert np.array_equal(seen["pf"].numpy(), z["v2_pitchf"])
+        op = OP.OraclePipeline(40000, 1, 6, 38, 41, hw, None, None, OW.V1_40K_CONFIG, noise_seed=0)
+        op.vc(torch.tensor([0]), audio0, pitch, pitchf, None, None, 0.0, "v1", 0.5)
+        assert seen["plen"] == int(z["v1_plen"]) and seen["phone"].shape[2] == 256 and np.array_equal(seen["phone"][0, :, ::16].numpy(), z["v1_phone"])
+    finally:
+        OP.OS.synth_infer = real_synth
+
+
+def _chunk_stub_vc(audio0, pitch, pitchf, window=160, upp=16):
+    """Same stand-in as tests/golden/make_golden.py::chunk_stub_vc (kept in step by the golden itself)."""
+    n = audio0.shape[0] // window
+    fr = np.asarray(audio0[: n * window], dtype=np.float32).astype(np.float64).reshape(n, window)      # vc casts to float32 first (pipeline.py:91-95)
+    v = fr.mean(1) + 0.25 * np.abs(fr).max(1)
+    if pitchf is not None:
+        m = min(n, pitchf.shape[1])
+        v[:m] += 1e-3 * pitchf[0, :m].double().numpy() + 1e-4 * pitch[0, :m].double().numpy()
+    return np.repeat(v, upp).astype(np.float32) * np.tile(np.linspace(0.5, 1.0, upp, dtype=np.float32), n)
+
+
+def test_pipeline_control_flow_oracle_matches_the_reference_method():
+    """oracle.pipeline.OraclePipeline.pipeline vs the reference's OWN ``Pipeline.pipeline`` (pipeline.py:186-366, executed from its source
+    with a deterministic stand-in for ``vc``): high-pass filter, silence-point search over a 10.3 s input (three cut points at x_max = 4 s),
+    per-chunk audio and pitch windows, x_pad trimming, concatenation, peak scaling; f0 and no-f0 models."""
+    from oracle import pipeline as OP, weights as OW
+    z = np.load(os.path.join(G, "pipeline_flow.npz"))
+    audio = OW.synth_voice(10.3, seed=14).numpy().astype(np.float32)
+    audio[40000:52000] *= 0.01; audio[90000:100000] *= 0.02
+    p_len = (audio.shape[0] + 2 * 16000) // 160
+    pitchf = (100.0 + np.arange(p_len) * 0.37).astype(np.float64)
+    pitch = (1 + np.arange(p_len) % 250).astype(np.int64)
+    cfg = list(OW.V2_48K_CONFIG); cfg[-1] = 1600
+    op = OP.OraclePipeline(1600, 1, 1, 3, 4, None, None, None, cfg, noise_seed=0)
+    op.vc = lambda sid, audio0, p, pf, *a, **k: _chunk_stub_vc(audio0, p, pf)
+    out = op.pipeline(0, audio.copy(), 0, (pitch, pitchf), None, 0.0, 2, 1600, 0, 1.0, "v2", 0.33)
+    assert out.shape[0] == int(z["n"]) and np.array_equal(out[::3].astype(np.float32), z["out"])
+    assert abs(float(np.abs(out.astype(np.float64)).sum()) - float(z["total"])) <= 1e-6 * float(z["total"])
+    out0 = op.pipeline(0, audio.copy(), 0, "rmvpe", None, 0.0, 0, 1600, 0, 1.0, "v2", 0.33)
+    assert out0.shape[0] == int(z["n_nof0"]) and np.array_equal(out0[::3].astype(np.float32), z["out_nof0"])
