@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinned where the reference can be executed here: ``phase_vocoder``, the SOLA step and the
 callback's input side (rings, TorchGate, cross-fade, resampling) are bit-equal to the reference's own statements run from its source
-(tests/golden/make_golden.py: phase_vocoder(), callback_pieces(); tests/test_oracle_golden.py).  ``RVC.infer`` (fairseq, faiss) and the
-envelope mix (librosa) are restatements.
+(tests/golden/make_golden.py: phase_vocoder(), callback_pieces(), rtrvc_glue(); tests/test_oracle_golden.py); ``OracleRVC.infer`` is
+bit-equal to the reference's own ``RVC.infer`` run from its source on duck-typed components (what reaches ``net_g.infer`` and the pitch
+ring, three consecutive blocks).  The envelope mix (librosa) is a restatement.
 
 Reference sites restated:
   RVC.__init__ state (pitch ring of 1024 frames)       infer/lib/rtrvc.py:63-66

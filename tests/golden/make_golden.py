@@ -339,7 +339,59 @@ def pipeline_flow():
                         total=np.float64(np.abs(out.astype(np.float64)).sum()), out_nof0=out0[::3].astype(np.float32), n_nof0=np.int64(out0.shape[0]))
 
 
+def rtrvc_glue():
+    """The reference's OWN realtime ``RVC.infer`` (infer/lib/rtrvc.py:134-260), cut out with ast (the module needs fairseq / faiss to
+    import) and run on a stand-in ``self``: hubert = the oracle HuBERT, index = the oracle IVF-Flat object, ``_get_f0`` = the oracle RMVPE
+    through the reference's own ``_get_f0`` body, net_g = a recorder.  Three consecutive rolling-window blocks pin the glue of row a17:
+    last-frame duplication, tail-only retrieval behind the ``(ix >= 0).all()`` guard, the pitch ring roll and ``pitch[3:-1]`` write, x2
+    up-sampling, what reaches ``net_g.infer``."""
+    import ast
+    import types
+    import torch.nn.functional as F_
+    from typing import Union, Optional, Literal
+    from torchaudio.transforms import Resample
+    from oracle import hubert as OH, ivf as OI, rmvpe as ORM
+    tree = ast.parse(open("/root/reference/infer/lib/rtrvc.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "RVC")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("infer", "_get_f0")]
+    ns = {"torch": torch, "np": np, "F": F_, "Union": Union, "Optional": Optional, "Literal": Literal, "Resample": Resample}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=fns, type_ignores=[])), "/root/reference/infer/lib/rtrvc.py", "exec"), ns)
+    hw, rw = OW.hubert_weights(777), OW.rmvpe_weights(4321)
+
+    class Model:
+        def extract_features(self, source, padding_mask, output_layer):
+            return (OH.extract_features(hw, source.float(), output_layer),)
+
+    class Recorder:
+        def infer(self, feats, p_len, sid, pitch=None, pitchf=None, skip_head=None, return_length=None, return_length2=None):
+            self.seen = dict(phone=feats.clone(), p_len=int(p_len[0]), pitch=pitch.clone(), pitchf=pitchf.clone(),
+                             args=(int(skip_head), int(return_length), int(return_length2)))
+            return torch.zeros(1, 1, return_length2 * 480)
+
+    class F0Gen:
+        def calculate(self, x, p_len, f0_up_key, method, filter_radius):
+            assert method == "rmvpe"
+            return ORM.calculate(rw, x.numpy(), None, f0_up_key)
+    idx = OI.build_ivf(OW.index_vectors(2000, 768, 1).numpy(), None, seed=0, exact_assign=True)
+    me = types.SimpleNamespace(is_half=False, device="cpu", version="v2", if_f0=1, hubert=Model(), index=idx,
+                               big_npy=idx.reconstruct_n(0, idx.ntotal), index_rate=0.5, window=160, formant_shift=0.0, f0_up_key=0,
+                               cache_pitch=torch.zeros(1024, dtype=torch.long), cache_pitchf=torch.zeros(1024, dtype=torch.float32),
+                               net_g=Recorder(), tgt_sr=48000, resample_kernel={}, f0_gen=F0Gen())
+    me._get_f0 = types.MethodType(ns["_get_f0"], me)
+    WIN, BLK, SKIP, RET = 43520, 2560, 250, 21
+    stream = OW.synth_voice(2.72 + 0.16 * 3 + 0.1, seed=9)
+    out = {}
+    for b in range(3):
+        ns["infer"](me, stream[b * BLK: b * BLK + WIN].clone(), BLK, SKIP, RET, "rmvpe")
+        seen = me.net_g.seen
+        out[f"phone{b}"] = seen["phone"][0, :, ::32].numpy()
+        out[f"pitch{b}"], out[f"pitchf{b}"] = seen["pitch"].numpy(), seen["pitchf"].numpy()
+        out[f"meta{b}"] = np.array([seen["p_len"], *seen["args"]], dtype=np.int64)
+    out["ring_pitch"], out["ring_pitchf"] = me.cache_pitch.numpy(), me.cache_pitchf.numpy()
+    np.savez_compressed(os.path.join(OUT, "rtrvc_glue.npz"), **out)
+
+
 if __name__ == "__main__":
-    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces(); vc_glue(); pipeline_flow()
+    synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces(); vc_glue(); pipeline_flow(); rtrvc_glue()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -231,3 +231,28 @@ def test_pipeline_control_flow_oracle_matches_the_reference_method():
     assert abs(float(np.abs(out.astype(np.float64)).sum()) - float(z["total"])) <= 1e-6 * float(z["total"])
     out0 = op.pipeline(0, audio.copy(), 0, "rmvpe", None, 0.0, 0, 1600, 0, 1.0, "v2", 0.33)
     assert out0.shape[0] == int(z["n_nof0"]) and np.array_equal(out0[::3].astype(np.float32), z["out_nof0"])
+
+
+def test_rtrvc_oracle_matches_the_reference_method():
+    """oracle.rtrvc.OracleRVC.infer vs the reference's OWN realtime ``RVC.infer`` (infer/lib/rtrvc.py:134-260, executed from its source
+    on duck-typed components by tests/golden/make_golden.py::rtrvc_glue) over three consecutive rolling-window blocks: what reaches the
+    synthesizer (features after last-frame duplication, tail-only retrieval, x2 up-sampling; the pitch-ring slices) and the ring itself."""
+    from oracle import ivf as OI, rtrvc as ORT, weights as OW
+    z = np.load(os.path.join(G, "rtrvc_glue.npz"))
+    hw, rw, sw = OW.hubert_weights(777), OW.rmvpe_weights(4321), OW.synth_weights(1234)
+    idx = OI.build_ivf(OW.index_vectors(2000, 768, 1).numpy(), None, seed=0, exact_assign=True)
+    real = ORT.OS.synth_infer
+    try:
+        ORT.OS.synth_infer = lambda w, cfg, feats, lens, sid, p, pf, n1, n2, **kw: torch.zeros(1, 1, kw["return_length2"] * 480)
+        orc = ORT.OracleRVC(hw, rw, sw, OW.V2_48K_CONFIG, idx, 0.5, key=0, noise_seed=0)
+        WIN, BLK, SKIP, RET = 43520, 2560, 250, 21
+        stream = OW.synth_voice(2.72 + 0.16 * 3 + 0.1, seed=9).numpy()
+        for b in range(3):
+            orc.infer(stream[b * BLK: b * BLK + WIN], BLK, SKIP, RET)
+            tap = orc.taps[-1]
+            assert list(z[f"meta{b}"]) == [tap["phone"].shape[1], SKIP, RET, RET]
+            assert np.array_equal(tap["phone"][0, :, ::32].numpy(), z[f"phone{b}"]), b
+            assert np.array_equal(tap["pitch"].numpy(), z[f"pitch{b}"]) and np.array_equal(tap["pitchf"].numpy(), z[f"pitchf{b}"]), b
+        assert np.array_equal(orc.cache_pitch.numpy(), z["ring_pitch"]) and np.array_equal(orc.cache_pitchf.numpy(), z["ring_pitchf"])
+    finally:
+        ORT.OS.synth_infer = real
