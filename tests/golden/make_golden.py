@@ -391,7 +391,41 @@ def rtrvc_glue():
     np.savez_compressed(os.path.join(OUT, "rtrvc_glue.npz"), **out)
 
 
+def rmvpe_compute_f0():
+    """The reference's OWN ``RMVPE.compute_f0 / _mel2hidden / _decode / _to_local_average_cents`` (rvc/f0/rmvpe.py:96-164), cut out with
+    ast (the module imports mel.py -> librosa) and attached to a stand-in that inherits the reference's importable ``F0Predictor``
+    (``_resize_f0``, ``_interpolate_f0``) and holds the reference's own ``E2E`` network; only the mel front end is the oracle's
+    (mel.py needs librosa.filters.mel).  Pins everything of row a8 downstream of the mel: padding to 32 frames, slicing, the
+    local-average-cents decode, threshold, resize and gap interpolation."""
+    import ast
+    import torch.nn.functional as F_
+    from typing import Optional, Union
+    from oracle import rmvpe as ORM
+    tree = ast.parse(open("/root/reference/rvc/f0/rmvpe.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "RMVPE")
+    want = ("compute_f0", "_mel2hidden", "_decode", "_to_local_average_cents")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert len(fns) == len(want)
+    ns = {"torch": torch, "np": np, "F": F_, "Optional": Optional, "Union": Union}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=fns, type_ignores=[])), "/root/reference/rvc/f0/rmvpe.py", "exec"), ns)
+    Stand = type("Stand", (F0Predictor,), {k: ns[k] for k in want})
+    me = Stand(160, 30, 8000, 16000, "cpu")
+    me.is_half = False
+    me.cents_mapping = np.pad(20 * np.arange(360) + 1997.3794084376191, (4, 4))          # rmvpe.py:62-63
+    net = E2E(4, 1, (2, 2)).eval()
+    net.load_state_dict(OW.rmvpe_weights(4321))
+    me.model = net
+    me.mel_extractor = lambda wav, center=True: ORM.log_mel(wav)
+    out = {}
+    for name, sec, seed in (("a", 1.0, 31), ("b", 0.73, 32)):
+        wav = OW.synth_voice(sec, seed=seed).numpy()
+        wav[int(0.4 * 16000): int(0.55 * 16000)] *= 1e-4                                   # an unvoiced gap to interpolate across
+        out[f"f0_{name}"] = np.asarray(me.compute_f0(wav, None, 0.03), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "rmvpe_compute_f0.npz"), **out)
+
+
 if __name__ == "__main__":
     synth(); rmvpe(); f0_fixtures(); hubert(); torchgate(); phase_vocoder(); callback_pieces(); vc_glue(); pipeline_flow(); rtrvc_glue()
+    rmvpe_compute_f0()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

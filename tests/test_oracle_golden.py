@@ -256,3 +256,19 @@ def test_rtrvc_oracle_matches_the_reference_method():
         assert np.array_equal(orc.cache_pitch.numpy(), z["ring_pitch"]) and np.array_equal(orc.cache_pitchf.numpy(), z["ring_pitchf"])
     finally:
         ORT.OS.synth_infer = real
+
+
+def test_rmvpe_compute_f0_oracle_matches_the_reference_methods():
+    """oracle.rmvpe.compute_f0 vs the reference's OWN RMVPE.compute_f0 / _mel2hidden / _decode / _to_local_average_cents (rmvpe.py:96-164,
+    executed from their source on the reference's own E2E network and F0Predictor base class; only the mel front end is the oracle's)."""
+    from oracle import rmvpe as ORM, weights as OW
+    z = np.load(os.path.join(G, "rmvpe_compute_f0.npz"))
+    w = OW.rmvpe_weights(4321)
+    for name, sec, seed in (("a", 1.0, 31), ("b", 0.73, 32)):
+        wav = OW.synth_voice(sec, seed=seed).numpy()
+        wav[int(0.4 * 16000): int(0.55 * 16000)] *= 1e-4
+        with torch.no_grad():
+            f0 = np.asarray(ORM.compute_f0(w, wav, None, 0.03), dtype=np.float64)
+        ref = z[f"f0_{name}"]
+        assert f0.shape == ref.shape and (ref > 0).any()
+        assert np.array_equal(f0 > 0, ref > 0) and np.abs(f0 - ref).max() <= 1e-6 * np.abs(ref).max(), (name, np.abs(f0 - ref).max())
